@@ -1,0 +1,151 @@
+/* spacecharge_b200.h -- C ABI of the B200-native space-charge hot path.
+ *
+ * Drop-in boundary for bmad-sim/SpaceCharge.jl v1.2.0 (paths below are relative to the
+ * reference root).  The reference has no FFI of its own: its boundary is the exported Julia
+ * surface `Mesh3D, deposit!, clear_mesh!, interpolate_field, solve!` (src/SpaceCharge.jl:17).
+ * A Julia shim (spacecharge.jl_b200/julia/SpaceChargeB200.jl) keeps that surface and `ccall`s
+ * the entry points declared here; the Python mirror (spacecharge.jl_b200/__init__.py) binds the
+ * same symbols through ctypes and is what the tests and bench.py drive.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns an int: 0 = SCB_OK, negative = scb_status error code; nothing
+ *     throws or exits.  scb_last_error(h) returns a human-readable message for the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller (never retained past the call)
+ *     unless the name says `_host`.  Work is enqueued asynchronously on the handle's stream;
+ *     call scb_sync() (or synchronise the stream yourself) before reading results.
+ *   - array layout is the reference's (Julia column-major): rho[ix + nx*(iy + ny*iz)],
+ *     efield[ix + nx*(iy + ny*(iz + nz*c))], c = 0,1,2; particles are separate x,y,z,q arrays.
+ *   - `pdt` is the element type of the particle arrays, `mdt` of the mesh arrays
+ *     (scb_dtype).  Arithmetic happens in promote(pdt, mdt) exactly as Julia promotes
+ *     (src/deposition.jl:39-41, src/interpolation.jl:31-33).
+ *   - geometry (min_bounds, max_bounds, delta, gamma, offset) is passed as double holding the
+ *     exact mdt-valued numbers stored in the Mesh3D struct (src/mesh.jl:19-34).
+ *   - a handle is bound to one device and one stream and is not thread-safe.
+ */
+#ifndef SPACECHARGE_B200_H
+#define SPACECHARGE_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SCB_API __attribute__((visibility("default")))
+#else
+#define SCB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scb_handle scb_handle;
+
+typedef enum scb_dtype { SCB_F32 = 0, SCB_F64 = 1 } scb_dtype;
+
+typedef enum scb_status {
+    SCB_OK = 0,
+    SCB_ERR_INVALID_ARG = -1,   /* null pointer, bad dtype, grid dim < 2, np < 0 ...            */
+    SCB_ERR_UNSUPPORTED = -2,   /* grid dimension beyond the supported padded FFT length        */
+    SCB_ERR_CUDA = -3,          /* a CUDA runtime call or kernel launch failed                  */
+    SCB_ERR_NO_DEVICE = -4,     /* no usable sm_100 device: there is NO CPU fallback            */
+    SCB_ERR_ALLOC = -5,         /* device workspace allocation failed                           */
+    SCB_ERR_COMM = -6           /* multi-GPU communicator failure                               */
+} scb_status;
+
+/* Library-level knobs (all optional; pass NULL for defaults). */
+typedef struct scb_options {
+    int32_t green_cache;       /* 1 (default): keep the IGF spectrum per geometry; 0: rebuild every
+                                  solve like the reference does (src/solvers/free_space.jl:79-89) */
+    int32_t deposit_mode;      /* 0 = auto, 1 = one thread per particle with global reductions     */
+    int32_t reserved[6];
+} scb_options;
+
+/* Per-stage device times of the most recent calls, in milliseconds (CUDA events on the
+ * handle's stream; valid after scb_sync).  Enabled with scb_enable_timing(h, 1). */
+typedef struct scb_timing {
+    float deposit_ms;
+    float solve_ms;
+    float interpolate_ms;
+    float green_ms;            /* time spent (re)building the IGF spectrum inside solve_ms        */
+    float pass_ms[8];          /* F1, F2, Z, B2, B3 of the last solve (rest reserved)             */
+} scb_timing;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+SCB_API int scb_version(void);
+SCB_API int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle** out);
+SCB_API int scb_destroy(scb_handle* h);
+SCB_API int scb_set_stream(scb_handle* h, void* cuda_stream);
+SCB_API int scb_sync(scb_handle* h);
+SCB_API const char* scb_last_error(const scb_handle* h);
+SCB_API int scb_enable_timing(scb_handle* h, int on);
+SCB_API int scb_get_timing(scb_handle* h, scb_timing* out);
+/* number of kernels this library has launched through the handle since creation */
+SCB_API int64_t scb_launch_count(const scb_handle* h);
+
+/* ---- a5: clear_mesh!  (src/deposition.jl:10-12) ------------------------------------------ */
+SCB_API int scb_clear(scb_handle* h, void* rho, const int64_t n[3], int mdt);
+
+/* ---- a6/a7: deposit!  (src/deposition.jl:28-86, 218-247) --------------------------------- */
+SCB_API int scb_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                const void* q, int pdt, void* rho, int mdt, const int64_t n[3],
+                const double min_bounds[3], const double delta[3], int clear);
+
+/* ---- a12/a13: solve!, solve_freespace!  (src/solvers/free_space.jl:14-47, 56-101) -------- */
+SCB_API int scb_solve(scb_handle* h, const void* rho, void* efield, int mdt, const int64_t n[3],
+              const double min_bounds[3], const double max_bounds[3], const double delta[3],
+              double gamma, int at_cathode);
+SCB_API int scb_solve_freespace(scb_handle* h, const void* rho, void* efield, int mdt,
+                        const int64_t n[3], const double delta[3], double gamma,
+                        const double offset[3]);
+
+/* ---- a14: interpolate_field  (src/interpolation.jl:17-128) -------------------------------- */
+SCB_API int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                    int pdt, const void* efield, int mdt, const int64_t n[3],
+                    const double min_bounds[3], const double delta[3],
+                    void* ex, void* ey, void* ez);
+
+/* ---- a8-a11: get_green_function!  (src/green_functions.jl:41-112), parity hook ----------- */
+/* Writes the integrated Green function in the reference's layout: a REAL array of shape
+ * n2 = (2nx, 2ny, 2nz) (the real part of the reference's complex cgrn; its imaginary part is
+ * zero), entry (i,j,k) for displacement (i+1-nx, j+1-ny, k+1-nz); the last plane of every
+ * dimension holds the raw point-wise values exactly like the reference leaves them.
+ * Always evaluated in double; `dt` selects the output element type. */
+SCB_API int scb_green(scb_handle* h, void* cgrn_real_out, const int64_t n2[3], const double delta[3],
+              double gamma, int icomp, const double offset[3], int dt);
+
+/* ---- a2: extrema for the auto-bounds constructor  (src/mesh.jl:120-122) ------------------ */
+/* Synchronous: returns host doubles holding the exact pdt-valued extrema. */
+SCB_API int scb_bounds(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+               int pdt, double out_min[3], double out_max[3]);
+
+/* ---- parity hook: particle -> cell indices (A.2), int64 outputs, unclamped ---------------- */
+SCB_API int scb_cell_index(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                   int pdt, int mdt, const double min_bounds[3], const double delta[3],
+                   int64_t* ix, int64_t* iy, int64_t* iz);
+
+/* ---- fused step on device-resident data: deposit! + solve! + interpolate_field ------------ */
+/* (the timed body of benchmark/full_pipeline_benchmark.jl:26-30) */
+SCB_API int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+             const void* q, int pdt, void* rho, void* efield, int mdt, const int64_t n[3],
+             const double min_bounds[3], const double max_bounds[3], const double delta[3],
+             double gamma, int at_cathode, void* ex, void* ey, void* ez);
+
+/* ---- the same step with HOST particle buffers (pinned or pageable) ------------------------ */
+/* Copies x,y,z,q host->device in chunks overlapped with deposition, solves, interpolates in
+ * chunks overlapped with the device->host copy of ex,ey,ez.  rho/efield stay on the device
+ * (pointers owned by the caller).  Synchronous on return. */
+SCB_API int scb_step_host(scb_handle* h, int64_t np, const void* x_host, const void* y_host,
+                  const void* z_host, const void* q_host, int pdt, void* rho, void* efield,
+                  int mdt, const int64_t n[3], const double min_bounds[3],
+                  const double max_bounds[3], const double delta[3], double gamma,
+                  int at_cathode, void* ex_host, void* ey_host, void* ez_host);
+
+/* ---- cache control ------------------------------------------------------------------------ */
+SCB_API int scb_drop_green_cache(scb_handle* h);
+/* bytes of device workspace currently owned by the handle */
+SCB_API int64_t scb_workspace_bytes(const scb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPACECHARGE_B200_H */

@@ -1,0 +1,409 @@
+"""spacecharge.jl_b200 -- host-side mirror of SpaceCharge.jl's public surface over the C ABI.
+
+The reference's whole API is five names (src/SpaceCharge.jl:17): ``Mesh3D, deposit!,
+clear_mesh!, interpolate_field, solve!``.  Julia is not installed in this image, so the tested
+host side is this Python twin of the Julia shim in ``julia/SpaceChargeB200.jl``: same names
+(``!`` spelled as a trailing underscore), same argument meaning, same error behaviour
+(``ErrorException`` with the reference's messages).  All computation happens in
+``lib/libspacecharge_b200.so`` (hand-written sm_100a CUDA); torch only provides device memory,
+streams and torch.distributed.  There is no CPU fallback.
+
+Arrays follow the reference's column-major layout: ``mesh.rho[ix, iy, iz]`` and
+``mesh.efield[ix, iy, iz, c]`` are torch views whose x index is the fastest in memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import LibraryMissing, ScbError  # noqa: F401
+
+__all__ = ["Mesh3D", "deposit_", "clear_mesh_", "interpolate_field", "solve_", "solve_freespace_",
+           "get_green_function_", "cell_indices", "step_", "step_host_", "ErrorException", "CLIGHT", "FPEI",
+           "Handle", "default_handle"]
+
+CLIGHT = 299792458.0          # src/utils.jl:7
+FPEI = CLIGHT ** 2 * 1.0e-7   # src/utils.jl:8
+
+
+class ErrorException(Exception):
+    """Julia's ``error("...")`` (src/mesh.jl:106-116, 206-211; src/deposition.jl:226-228)."""
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_dtype(T):
+    torch = _torch()
+    if T in (np.float32, "float32", "Float32", torch.float32):
+        return np.float32
+    if T in (np.float64, "float64", "Float64", float, torch.float64):
+        return np.float64
+    raise ErrorException("T must be Float32 or Float64")
+
+
+def _torch_dtype(npdt):
+    torch = _torch()
+    return torch.float32 if np.dtype(npdt) == np.float32 else torch.float64
+
+
+def _tag(torch_dtype):
+    torch = _torch()
+    if torch_dtype == torch.float32:
+        return _lib.SCB_F32
+    if torch_dtype == torch.float64:
+        return _lib.SCB_F64
+    raise ErrorException("only Float32 and Float64 arrays are supported")
+
+
+# ------------------------------------------------------------------------------------ handle
+class Handle:
+    """One ``scb_handle`` per (device, stream-in-use).  Not thread-safe (same as the C ABI)."""
+
+    def __init__(self, device: int = 0, green_cache: bool = True):
+        torch = _torch()
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise LibraryMissing("no CUDA device: spacecharge.jl_b200 has no CPU fallback")
+        self.device = int(device)
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream
+        opt = _lib.scb_options()
+        opt.green_cache = 1 if green_cache else 0
+        h = C.c_void_p()
+        rc = self.lib.scb_create(self.device, C.c_void_p(self._stream), C.byref(opt), C.byref(h))
+        if rc != 0:
+            raise ScbError(rc, "scb_create failed (an sm_100 GPU is required)")
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise ScbError(rc, self.lib.scb_last_error(self.h).decode())
+
+    def use_current_stream(self):
+        s = _torch().cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            self.check(self.lib.scb_set_stream(self.h, C.c_void_p(s)))
+            self._stream = s
+
+    def sync(self):
+        self.check(self.lib.scb_sync(self.h))
+
+    def enable_timing(self, on=True):
+        self.check(self.lib.scb_enable_timing(self.h, 1 if on else 0))
+
+    def timing(self) -> dict:
+        t = _lib.scb_timing()
+        self.check(self.lib.scb_get_timing(self.h, C.byref(t)))
+        return {"deposit_ms": t.deposit_ms, "solve_ms": t.solve_ms, "interpolate_ms": t.interpolate_ms,
+                "green_ms": t.green_ms, "pass_ms": list(t.pass_ms)[:5]}
+
+    def launch_count(self) -> int:
+        return int(self.lib.scb_launch_count(self.h))
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.scb_workspace_bytes(self.h))
+
+    def drop_green_cache(self):
+        self.check(self.lib.scb_drop_green_cache(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.scb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def default_handle(device: Optional[int] = None) -> Handle:
+    torch = _torch()
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]
+
+
+# ------------------------------------------------------------------------------------- mesh
+def _device_array(a, device):
+    """Particle array -> 1-D contiguous CUDA tensor (the reference takes CuArrays; host arrays
+    are uploaded like ``CuArray(x)``)."""
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        arr = np.asarray(a)
+        if arr.dtype.kind != "f" or arr.dtype.itemsize not in (4, 8):
+            arr = arr.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    if t.device.type != "cuda":
+        t = t.to("cuda:%d" % device)
+    return t.contiguous().view(-1)
+
+
+def _extrema_host(a):
+    arr = np.asarray(a)
+    if arr.dtype.kind != "f" or arr.dtype.itemsize not in (4, 8):
+        arr = arr.astype(np.float64)
+    return arr.dtype.type(arr.min()), arr.dtype.type(arr.max()), arr.dtype.type
+
+
+class Mesh3D:
+    """src/mesh.jl:19-34.  Two constructors, selected like Julia's dispatch:
+
+    ``Mesh3D(grid_size, particles_x, particles_y, particles_z; T, gamma, total_charge)``
+        bounds from the particle extrema (src/mesh.jl:95-174)
+    ``Mesh3D(grid_size, min_bounds, max_bounds; T, gamma, total_charge)``
+        manual bounds (src/mesh.jl:196-238)
+    """
+
+    def __init__(self, grid_size: Sequence[int], *args, T=np.float64, gamma: float = 1.0,
+                 total_charge: float = 0.0, device: Optional[int] = None, handle: Optional[Handle] = None,
+                 group=None):
+        torch = _torch()
+        grid_size = tuple(int(g) for g in grid_size)
+        if len(grid_size) != 3:
+            raise ErrorException("grid_size must have three elements")
+        npdt = _np_dtype(T)
+        Tn = np.dtype(npdt).type
+        if any(g <= 1 for g in grid_size):
+            raise ErrorException("All elements of grid_size must be at least 2.")
+        if len(args) == 2:
+            lo, hi = args
+            if any(h <= l for h, l in zip(hi, lo)):
+                raise ErrorException("max_bounds must be strictly greater than min_bounds for all dimensions.")
+            lo = tuple(Tn(v) for v in lo)
+            hi = tuple(Tn(v) for v in hi)
+            delta = tuple(Tn((h - l) / Tn(n - 1)) for h, l, n in zip(hi, lo, grid_size))  # :214-220
+            dev_hint = None
+        elif len(args) == 3:
+            px, py, pz = args
+            if len(px) == 0 or len(py) == 0 or len(pz) == 0:
+                raise ErrorException("Particle arrays cannot be empty.")
+            if not (len(px) == len(py) == len(pz)):
+                raise ErrorException("Particle coordinate arrays must have the same length.")
+            dev_hint = px.device.index if isinstance(px, torch.Tensor) and px.device.type == "cuda" else None
+            lo, hi, delta = self._auto_bounds(grid_size, px, py, pz, Tn, dev_hint if device is None else device, handle)
+        else:
+            raise ErrorException("Mesh3D(grid_size, x, y, z) or Mesh3D(grid_size, min_bounds, max_bounds)")
+        if device is None:
+            device = dev_hint if dev_hint is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.grid_size = grid_size
+        self.min_bounds = lo
+        self.max_bounds = hi
+        self.delta = delta
+        self.gamma = Tn(gamma)
+        self.total_charge = Tn(total_charge)
+        self.T = npdt
+        self.device = int(device)
+        self.handle = handle if handle is not None else default_handle(self.device)
+        self.group = group  # torch.distributed process group for particle-sharded runs (or None)
+        nx, ny, nz = grid_size
+        td = _torch_dtype(npdt)
+        dev = "cuda:%d" % self.device
+        self._rho = torch.zeros((nz, ny, nx), dtype=td, device=dev)
+        self._efield = torch.zeros((3, nz, ny, nx), dtype=td, device=dev)
+        self._workspace = None
+
+    @staticmethod
+    def _auto_bounds(grid_size, px, py, pz, Tn, device, handle):
+        """src/mesh.jl:118-156: extrema and first delta in the particles' precision, the 1e-6
+        padding and the final delta in Float64, zero delta -> 1e-6, then the cast to T."""
+        torch = _torch()
+        ext = []
+        if all(isinstance(p, torch.Tensor) and p.device.type == "cuda" for p in (px, py, pz)):
+            hd = handle if handle is not None else default_handle(px.device.index)
+            hd.use_current_stream()
+            x, y, z = (p.contiguous().view(-1) for p in (px, py, pz))
+            if not (x.dtype == y.dtype == z.dtype):
+                raise ErrorException("particle coordinate arrays must share one element type")
+            omin, omax = _lib.f64x3((0, 0, 0)), _lib.f64x3((0, 0, 0))
+            hd.check(hd.lib.scb_bounds(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype), omin, omax))
+            P = np.float32 if x.dtype == torch.float32 else np.float64
+            ext = [(P(omin[a]), P(omax[a]), P) for a in range(3)]
+        else:
+            for p in (px, py, pz):
+                if isinstance(p, torch.Tensor):
+                    p = p.detach().cpu().numpy()
+                ext.append(_extrema_host(p))
+        lo1, hi1, d1 = [], [], []
+        for (lo, hi, P), n in zip(ext, grid_size):
+            d0 = P((hi - lo) / P(n - 1))
+            l = np.float64(lo) - 1e-6 * np.float64(d0)
+            h = np.float64(hi) + 1e-6 * np.float64(d0)
+            d = (h - l) / np.float64(n - 1)
+            if d == 0:
+                d = np.float64(1e-6)
+            lo1.append(Tn(l))
+            hi1.append(Tn(h))
+            d1.append(Tn(d))
+        return tuple(lo1), tuple(hi1), tuple(d1)
+
+    # column-major views, indexable like the reference's arrays (0-based)
+    @property
+    def rho(self):
+        return self._rho.permute(2, 1, 0)
+
+    @property
+    def efield(self):
+        return self._efield.permute(3, 2, 1, 0)
+
+    def __repr__(self):  # src/mesh.jl:240-246
+        nx, ny, nz = self.grid_size
+        lo, hi = self.min_bounds, self.max_bounds
+        return ("Mesh3D{%s, CudaTensor} (%dx%dx%d) bounds=[(%s,%s,%s), (%s,%s,%s)] gamma=%s"
+                % (np.dtype(self.T).name, nx, ny, nz, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], self.gamma))
+
+    # helpers for the ABI calls
+    def _n(self):
+        return _lib.i64x3(self.grid_size)
+
+    def _lo(self):
+        return _lib.f64x3(self.min_bounds)
+
+    def _hi(self):
+        return _lib.f64x3(self.max_bounds)
+
+    def _d(self):
+        return _lib.f64x3(self.delta)
+
+    def _mdt(self):
+        return _lib.SCB_F32 if self.T == np.float32 else _lib.SCB_F64
+
+
+# -------------------------------------------------------------------------------- operations
+def clear_mesh_(mesh: Mesh3D) -> None:
+    """clear_mesh!  (src/deposition.jl:10-12)"""
+    hd = mesh.handle
+    hd.use_current_stream()
+    hd.check(hd.lib.scb_clear(hd.h, mesh._rho.data_ptr(), mesh._n(), mesh._mdt()))
+
+
+def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, clear: bool = True) -> None:
+    """deposit!  (src/deposition.jl:218-247).  With ``mesh.group`` set (particle-sharded run) the
+    local charge grids are summed over the ranks afterwards."""
+    if not (len(particles_x) == len(particles_y) == len(particles_z) == len(particles_q)):
+        raise ErrorException("Particle coordinate and charge arrays must have the same length.")
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z, q = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z, particles_q))
+    if not (x.dtype == y.dtype == z.dtype == q.dtype):
+        raise ErrorException("particle arrays must share one element type")
+    hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
+                                mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
+    if mesh.group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(mesh._rho, group=mesh.group)
+
+
+def solve_(mesh: Mesh3D, at_cathode: bool = False) -> None:
+    """solve!  (src/solvers/free_space.jl:14-47)"""
+    hd = mesh.handle
+    hd.use_current_stream()
+    hd.check(hd.lib.scb_solve(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(),
+                              mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0))
+
+
+def solve_freespace_(mesh: Mesh3D, offset=(0.0, 0.0, 0.0)) -> None:
+    """solve_freespace!  (src/solvers/free_space.jl:56-101)"""
+    hd = mesh.handle
+    hd.use_current_stream()
+    Tn = np.dtype(mesh.T).type
+    off = tuple(float(Tn(v)) for v in offset)
+    hd.check(hd.lib.scb_solve_freespace(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(),
+                                        mesh._d(), float(mesh.gamma), _lib.f64x3(off)))
+
+
+def interpolate_field(mesh: Mesh3D, particles_x, particles_y, particles_z):
+    """interpolate_field  (src/interpolation.jl:100-128): returns (Ex, Ey, Ez) with the particles'
+    element type, freshly allocated like ``similar(particles_x)``."""
+    torch = _torch()
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    if not (x.dtype == y.dtype == z.dtype):
+        raise ErrorException("particle arrays must share one element type")
+    ex, ey, ez = (torch.empty_like(x) for _ in range(3))
+    hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                    mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                    ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+    return ex, ey, ez
+
+
+def get_green_function_(shape2, delta, gamma, icomp: int, offset=(0.0, 0.0, 0.0), T=np.float64,
+                        handle: Optional[Handle] = None):
+    """get_green_function!  (src/green_functions.jl:41-67): the real part of the reference's cgrn
+    array of shape (2nx, 2ny, 2nz), as a column-major torch view."""
+    torch = _torch()
+    hd = handle if handle is not None else default_handle()
+    hd.use_current_stream()
+    npdt = _np_dtype(T)
+    sx, sy, sz = (int(v) for v in shape2)
+    out = torch.empty((sz, sy, sx), dtype=_torch_dtype(npdt), device="cuda:%d" % hd.device)
+    hd.check(hd.lib.scb_green(hd.h, out.data_ptr(), _lib.i64x3((sx, sy, sz)), _lib.f64x3(delta), float(gamma), int(icomp),
+                              _lib.f64x3(offset), _lib.SCB_F32 if npdt == np.float32 else _lib.SCB_F64))
+    return out.permute(2, 1, 0)
+
+
+def cell_indices(mesh: Mesh3D, particles_x, particles_y, particles_z):
+    """Parity hook: floor((p - min) / delta) per axis as int64."""
+    torch = _torch()
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    ix, iy, iz = (torch.empty(x.numel(), dtype=torch.int64, device=x.device) for _ in range(3))
+    hd.check(hd.lib.scb_cell_index(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype), mesh._mdt(),
+                                   mesh._lo(), mesh._d(), ix.data_ptr(), iy.data_ptr(), iz.data_ptr()))
+    return ix, iy, iz
+
+
+def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
+    """deposit! + solve! + interpolate_field on device-resident tensors with caller-owned outputs
+    (the timed body of benchmark/full_pipeline_benchmark.jl:26-30, without the per-call allocation)."""
+    hd = mesh.handle
+    hd.use_current_stream()
+    if mesh.group is None:
+        hd.check(hd.lib.scb_step(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
+                                 mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(),
+                                 mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0,
+                                 ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+        return
+    deposit_(mesh, x, y, z, q)
+    solve_(mesh, at_cathode=at_cathode)
+    hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                    mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                    ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+
+
+def step_host_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
+    """The same step with HOST particle buffers (numpy arrays or CPU torch tensors, ideally
+    pinned): host->device and device->host copies are part of the call (scb_step_host)."""
+    torch = _torch()
+    hd = mesh.handle
+    hd.use_current_stream()
+
+    def ptr(a):
+        if isinstance(a, torch.Tensor):
+            assert a.device.type == "cpu" and a.is_contiguous()
+            return a.data_ptr(), a.dtype
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, (torch.float32 if a.dtype == np.float32 else torch.float64)
+
+    (px, dt), (py, _), (pz, _), (pq, _) = ptr(x), ptr(y), ptr(z), ptr(q)
+    (pex, _), (pey, _), (pez, _) = ptr(ex), ptr(ey), ptr(ez)
+    hd.check(hd.lib.scb_step_host(hd.h, len(x), px, py, pz, pq, _tag(dt), mesh._rho.data_ptr(), mesh._efield.data_ptr(),
+                                  mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma),
+                                  1 if at_cathode else 0, pex, pey, pez))

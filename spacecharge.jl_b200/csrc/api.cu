@@ -1,0 +1,903 @@
+// api.cu -- C ABI (include/spacecharge_b200.h): handle, workspace, Green-spectrum cache and the
+// orchestration of the pass kernels.  No CPU fallback anywhere: every entry point either
+// launches the sm_100a kernels or returns an error code.
+#include "../../include/spacecharge_b200.h"
+#include "fft_passes.cuh"
+#include "kernels.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace scb;
+
+namespace {
+
+constexpr double kCLight = 299792458.0;            // src/utils.jl:7
+constexpr double kFPEI = kCLight * kCLight * 1e-7;  // src/utils.jl:8
+constexpr int kMaxFftLen = 2048;
+constexpr int kMaxGreenEntries = 4;
+
+struct GreenKey {
+    int n[3];
+    double delta[3];
+    double gamma;
+    double offset[3];
+    int mdt;
+    int kind;  // 0: free-space compressed S, 1: image (corr along z, negated) full, 2: general full
+    bool operator==(const GreenKey& o) const {
+        for (int a = 0; a < 3; ++a)
+            if (n[a] != o.n[a] || delta[a] != o.delta[a] || offset[a] != o.offset[a]) return false;
+        return gamma == o.gamma && mdt == o.mdt && kind == o.kind;
+    }
+};
+
+struct GreenEntry {
+    GreenKey key;
+    void* data = nullptr;
+    size_t bytes = 0;
+    long long scomp = 0;
+    unsigned long long stamp = 0;
+};
+
+}  // namespace
+
+struct scb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    scb_options opt{};
+    std::string err;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::map<std::pair<int, int>, void*> twiddles;  // (N, is_f64) -> device table of N roots
+    std::vector<GreenEntry> green;
+    unsigned long long stamp = 0;
+    unsigned long long* d_bounds = nullptr;
+    int64_t launches = 0;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[16]{};
+    bool ev_ready = false;
+    scb_timing last{};
+    bool t_dep = false, t_solve = false, t_interp = false, t_green = false, t_pass = false;
+    // host-step staging
+    cudaStream_t copy_stream = nullptr;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    std::vector<cudaEvent_t> chunk_ev;
+};
+
+namespace {
+
+int fail(scb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+int cuda_fail(scb_handle* h, cudaError_t e, const char* where) {
+    return fail(h, SCB_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define SCB_CUDA(h, call)                                   \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__, #call); \
+    } while (0)
+
+#define SCB_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != SCB_OK) return rc__; \
+    } while (0)
+
+int padded_len(int n) {
+    int L = 8;
+    while (L < 2 * n) L *= 2;
+    return L;
+}
+
+bool valid_dt(int dt) { return dt == SCB_F32 || dt == SCB_F64; }
+size_t dt_size(int dt) { return dt == SCB_F64 ? 8 : 4; }
+
+int check_grid(scb_handle* h, const int64_t n[3]) {
+    if (!n) return fail(h, SCB_ERR_INVALID_ARG, "grid size pointer is null");
+    for (int a = 0; a < 3; ++a) {
+        if (n[a] < 2) return fail(h, SCB_ERR_INVALID_ARG, "All elements of grid_size must be at least 2.");
+        if (2 * n[a] > kMaxFftLen) return fail(h, SCB_ERR_UNSUPPORTED, "grid dimension larger than 1024 is not supported");
+    }
+    return SCB_OK;
+}
+
+int ensure_arena(scb_handle* h, size_t bytes) {
+    if (bytes <= h->arena_bytes) return SCB_OK;
+    if (h->arena) {
+        SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+        SCB_CUDA(h, cudaFree(h->arena));
+        h->arena = nullptr;
+        h->arena_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&h->arena, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, SCB_ERR_ALLOC, "workspace allocation of " + std::to_string(bytes) + " bytes failed");
+    }
+    h->arena_bytes = bytes;
+    return SCB_OK;
+}
+
+template <typename T>
+int get_twiddles(scb_handle* h, int N, const cx_t<T>** out) {
+    const int is64 = sizeof(T) == 8;
+    auto it = h->twiddles.find({N, is64});
+    if (it != h->twiddles.end()) {
+        *out = static_cast<const cx_t<T>*>(it->second);
+        return SCB_OK;
+    }
+    std::vector<cx_t<T>> host(N);
+    for (int k = 0; k < N; ++k) {
+        // exact octant symmetry is not needed; long double keeps the table correctly rounded
+        const long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)k / (long double)N;
+        host[k].x = (T)cosl(a);
+        host[k].y = (T)sinl(a);
+    }
+    void* d = nullptr;
+    SCB_CUDA(h, cudaMalloc(&d, sizeof(cx_t<T>) * N));
+    SCB_CUDA(h, cudaMemcpy(d, host.data(), sizeof(cx_t<T>) * N, cudaMemcpyHostToDevice));
+    h->twiddles[{N, is64}] = d;
+    *out = static_cast<const cx_t<T>*>(d);
+    return SCB_OK;
+}
+
+void tick(scb_handle* h, int i) {
+    if (h->timing && h->ev_ready) cudaEventRecord(h->ev[i], h->stream);
+}
+
+struct Plan {
+    int n[3];
+    int L[3];
+    int PX, ninner;
+};
+
+Plan make_plan(const int64_t n[3]) {
+    Plan p;
+    for (int a = 0; a < 3; ++a) {
+        p.n[a] = (int)n[a];
+        p.L[a] = padded_len((int)n[a]);
+    }
+    p.ninner = p.L[0] / 2 + 1;
+    p.PX = (p.ninner + 7) / 8 * 8;
+    return p;
+}
+
+// ---- Green spectrum: build (cold) and cache ------------------------------------------------
+int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& ent) {
+    IgfGeom g{};
+    for (int a = 0; a < 3; ++a) {
+        g.n[a] = pl.n[a];
+        g.L[a] = pl.L[a];
+        g.isize[a] = 2 * pl.n[a];
+        g.delta[a] = key.delta[a];
+        g.offset[a] = key.offset[a];
+        g.sym[a] = key.offset[a] == 0.0 ? 1 : 0;
+        g.corr[a] = 0;
+    }
+    g.gamma = key.gamma;
+    double sign_all = 1.0;
+    if (key.kind == 1) {  // image charge: correlation along z, negated (src/solvers/free_space.jl:34)
+        g.corr[2] = 1;
+        g.sym[2] = 0;
+        sign_all = -1.0;
+    }
+    for (int a = 0; a < 3; ++a) {
+        g.i0[a] = g.sym[a] ? pl.n[a] : 1;
+        g.cnt[a] = g.sym[a] ? pl.n[a] + 1 : 2 * pl.n[a];
+    }
+    const size_t nP = (size_t)g.cnt[0] * g.cnt[1] * g.cnt[2];
+    const size_t nG = (size_t)pl.L[0] * pl.L[1] * pl.L[2];
+    const size_t nS = (size_t)pl.PX * pl.L[1] * pl.L[2];
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t need = al(nP * 8) + al(nG * 8) + al(nS * 16);
+    SCB_TRY(ensure_arena(h, need));
+    char* base = static_cast<char*>(h->arena);
+    double* P = reinterpret_cast<double*>(base);
+    double* G = reinterpret_cast<double*>(base + al(nP * 8));
+    double2* spec = reinterpret_cast<double2*>(base + al(nP * 8) + al(nG * 8));
+
+    const bool f64 = key.mdt == SCB_F64;
+    size_t per_comp;  // elements
+    if (key.kind == 0) per_comp = (size_t)pl.PX * (pl.L[1] / 2 + 1) * (pl.L[2] / 2 + 1);
+    else per_comp = nS;
+    const size_t elem = (key.kind == 0 ? 1 : 2) * dt_size(key.mdt);
+    ent.bytes = 3 * per_comp * elem;
+    ent.scomp = (long long)per_comp;
+    cudaError_t e = cudaMalloc(&ent.data, ent.bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        ent.data = nullptr;
+        return fail(h, SCB_ERR_ALLOC, "Green-spectrum allocation failed");
+    }
+
+    const double2 *twx, *twy, *twz;
+    SCB_TRY(get_twiddles<double>(h, pl.L[0], &twx));
+    SCB_TRY(get_twiddles<double>(h, pl.L[1], &twy));
+    SCB_TRY(get_twiddles<double>(h, pl.L[2], &twz));
+
+    for (int c = 0; c < 3; ++c) {
+        SCB_CUDA(h, launch_green_point(P, g, c + 1, h->stream));
+        SCB_CUDA(h, launch_green_place(G, P, g, c + 1, sign_all, h->stream));
+        XParams<double> xp{};
+        xp.in = G;
+        xp.out = spec;
+        xp.tw = twx;
+        xp.nlines = (long long)pl.L[1] * pl.L[2];
+        xp.real_sline = pl.L[0];
+        xp.n_real = pl.L[0];
+        xp.PX = pl.PX;
+        xp.scale = 1.0;
+        SCB_CUDA(h, launch_x_r2c<double>(pl.L[0], xp, 1, h->stream));
+        LinesParams<double> yp{};
+        yp.in = spec;
+        yp.out = spec;
+        yp.tw = twy;
+        yp.n_in = yp.n_out = pl.L[1];
+        yp.ninner = pl.ninner;
+        yp.in_sline = yp.out_sline = pl.PX;
+        yp.in_souter = yp.out_souter = (long long)pl.PX * pl.L[1];
+        yp.scale = 1.0;
+        SCB_CUDA(h, launch_lines<double>(pl.L[1], -1, yp, pl.L[2], 1, h->stream));
+        LinesParams<double> zp{};
+        zp.in = spec;
+        zp.out = spec;
+        zp.tw = twz;
+        zp.n_in = zp.n_out = pl.L[2];
+        zp.ninner = pl.ninner;
+        zp.in_sline = zp.out_sline = (long long)pl.PX * pl.L[1];
+        zp.in_souter = zp.out_souter = pl.PX;
+        zp.scale = 1.0;
+        SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, pl.L[1], 1, h->stream));
+        char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
+        if (key.kind == 0)
+            SCB_CUDA(h, launch_green_compress_free(dst, f64, spec, pl.ninner, pl.PX, pl.L[1], pl.L[2], h->stream));
+        else
+            SCB_CUDA(h, launch_green_convert_full(dst, f64, spec, pl.ninner, pl.PX, (long long)nS, h->stream));
+        h->launches += 6;
+    }
+    return SCB_OK;
+}
+
+void free_green(scb_handle* h) {
+    for (auto& e : h->green)
+        if (e.data) cudaFree(e.data);
+    h->green.clear();
+}
+
+int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEntry** out) {
+    if (h->opt.green_cache) {
+        for (auto& e : h->green) {
+            if (e.key == key) {
+                e.stamp = ++h->stamp;
+                *out = &e;
+                return SCB_OK;
+            }
+        }
+    } else {
+        // reference behaviour: the Green function is recomputed on every solve
+        for (size_t i = 0; i < h->green.size();) {
+            if (h->green[i].key.kind == key.kind) {
+                SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+                cudaFree(h->green[i].data);
+                h->green.erase(h->green.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+    }
+    if ((int)h->green.size() >= kMaxGreenEntries) {
+        size_t victim = 0;
+        for (size_t i = 1; i < h->green.size(); ++i)
+            if (h->green[i].stamp < h->green[victim].stamp) victim = i;
+        SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->green[victim].data);
+        h->green.erase(h->green.begin() + victim);
+    }
+    GreenEntry ent;
+    ent.key = key;
+    ent.stamp = ++h->stamp;
+    tick(h, 6);
+    int rc = build_green(h, pl, key, ent);
+    tick(h, 7);
+    h->t_green = true;
+    if (rc != SCB_OK) {
+        if (ent.data) cudaFree(ent.data);
+        return rc;
+    }
+    h->green.push_back(ent);
+    *out = &h->green.back();
+    return SCB_OK;
+}
+
+GreenKey make_key(const Plan& pl, const double delta[3], double gamma, const double offset[3], int mdt, int kind) {
+    GreenKey k;
+    std::memset(&k, 0, sizeof(k));
+    for (int a = 0; a < 3; ++a) {
+        k.n[a] = pl.n[a];
+        k.delta[a] = delta[a];
+        k.offset[a] = offset[a] == 0.0 ? 0.0 : offset[a];  // fold -0.0
+    }
+    k.gamma = gamma;
+    k.mdt = mdt;
+    k.kind = kind;
+    return k;
+}
+
+// ---- the convolution -----------------------------------------------------------------------
+// mode 0: free space; mode 1: free space + cathode image (offset_z given); mode 2: general offset
+template <typename T>
+int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const double delta[3], double gamma,
+              int mode, const double offset[3]) {
+    using C = cx_t<T>;
+    const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
+    const double zero3[3] = {0, 0, 0};
+    const GreenEntry* gfree = nullptr;
+    const GreenEntry* gaux = nullptr;
+    h->t_green = false;
+    // the builds use the arena as scratch, so they must come before the passes touch it
+    if (mode == 0 || mode == 1) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, zero3, mdt, 0), &gfree));
+    if (mode == 1) {
+        SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 1), &gaux));
+        // get_green may have reallocated the vector
+        for (auto& e : h->green)
+            if (e.key == make_key(pl, delta, gamma, zero3, mdt, 0)) gfree = &e;
+    }
+    if (mode == 2) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 2), &gaux));
+
+    const size_t szA = (size_t)pl.PX * pl.n[1] * pl.n[2];
+    const size_t szB = (size_t)pl.PX * pl.L[1] * pl.n[2];
+    SCB_TRY(ensure_arena(h, (4 * szA + 4 * szB) * sizeof(C)));
+    C* A = static_cast<C*>(h->arena);
+    C* B = A + szA;
+    C* Cc = B + szB;
+    C* D = Cc + 3 * szB;
+
+    const C *twx, *twy, *twz;
+    SCB_TRY(get_twiddles<T>(h, pl.L[0], &twx));
+    SCB_TRY(get_twiddles<T>(h, pl.L[1], &twy));
+    SCB_TRY(get_twiddles<T>(h, pl.L[2], &twz));
+
+    tick(h, 8);
+    {  // F1
+        XParams<T> p{};
+        p.in = rho;
+        p.out = A;
+        p.tw = twx;
+        p.nlines = (long long)pl.n[1] * pl.n[2];
+        p.real_sline = pl.n[0];
+        p.n_real = pl.n[0];
+        p.PX = pl.PX;
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_x_r2c<T>(pl.L[0], p, 1, h->stream));
+    }
+    tick(h, 9);
+    {  // F2
+        LinesParams<T> p{};
+        p.in = A;
+        p.out = B;
+        p.tw = twy;
+        p.n_in = pl.n[1];
+        p.n_out = pl.L[1];
+        p.ninner = pl.ninner;
+        p.in_sline = pl.PX;
+        p.in_souter = (long long)pl.PX * pl.n[1];
+        p.out_sline = pl.PX;
+        p.out_souter = (long long)pl.PX * pl.L[1];
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], -1, p, pl.n[2], 1, h->stream));
+    }
+    tick(h, 10);
+    {  // Z
+        ZParams<T> p{};
+        p.in = B;
+        p.out = Cc;
+        p.tw = twz;
+        p.out_scomp = (long long)szB;
+        p.nz = pl.n[2];
+        p.ninner = pl.ninner;
+        p.PX = pl.PX;
+        p.Ly = pl.L[1];
+        if (gfree) {
+            p.S = static_cast<const T*>(gfree->data);
+            p.S_scomp = gfree->scomp;
+        }
+        if (gaux) {
+            p.H = static_cast<const C*>(gaux->data);
+            p.H_scomp = gaux->scomp;
+        }
+        const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
+        SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
+    }
+    tick(h, 11);
+    {  // B2
+        LinesParams<T> p{};
+        p.in = Cc;
+        p.out = D;
+        p.tw = twy;
+        p.n_in = pl.L[1];
+        p.n_out = pl.n[1];
+        p.ninner = pl.ninner;
+        p.in_sline = pl.PX;
+        p.in_souter = (long long)pl.PX * pl.L[1];
+        p.out_sline = pl.PX;
+        p.out_souter = (long long)pl.PX * pl.n[1];
+        p.in_scomp = (long long)szB;
+        p.out_scomp = (long long)szA;
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, pl.n[2], 3, h->stream));
+    }
+    tick(h, 12);
+    {  // B3
+        XParams<T> p{};
+        p.in = D;
+        p.out = efield;
+        p.tw = twx;
+        p.nlines = (long long)pl.n[1] * pl.n[2];
+        p.real_sline = pl.n[0];
+        p.n_real = pl.n[0];
+        p.PX = pl.PX;
+        p.real_scomp = (long long)pl.n[0] * pl.n[1] * pl.n[2];
+        p.cplx_scomp = (long long)szA;
+        // factr = T(FPEI) (src/solvers/free_space.jl:75) times the inverse-FFT 1/M (:95)
+        p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
+        SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
+    }
+    tick(h, 13);
+    h->t_pass = true;
+    h->launches += 5;
+    return SCB_OK;
+}
+
+int solve_dispatch(scb_handle* h, const void* rho, void* efield, int mdt, const int64_t n[3], const double delta[3],
+                   double gamma, int mode, const double offset[3]) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!rho || !efield || !delta) return fail(h, SCB_ERR_INVALID_ARG, "null pointer argument");
+    if (!valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad mesh dtype");
+    SCB_TRY(check_grid(h, n));
+    for (int a = 0; a < 3; ++a)
+        if (!(delta[a] > 0.0)) return fail(h, SCB_ERR_INVALID_ARG, "delta must be positive");
+    if (!(gamma > 0.0)) return fail(h, SCB_ERR_INVALID_ARG, "gamma must be positive");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    const Plan pl = make_plan(n);
+    tick(h, 2);
+    int rc;
+    if (mdt == SCB_F64) rc = run_solve<double>(h, (const double*)rho, (double*)efield, pl, delta, gamma, mode, offset);
+    else rc = run_solve<float>(h, (const float*)rho, (float*)efield, pl, delta, gamma, mode, offset);
+    tick(h, 3);
+    h->t_solve = rc == SCB_OK;
+    return rc;
+}
+
+Geom3 make_geom(const int64_t n[3], const double lo[3], const double delta[3]) {
+    Geom3 g;
+    for (int a = 0; a < 3; ++a) {
+        g.n[a] = (int)n[a];
+        g.lo[a] = lo[a];
+        g.delta[a] = delta[a];
+    }
+    return g;
+}
+
+double image_offset_z(int mdt, double min_z, double max_z) {
+    // offset_z = 2*min_z + (max_z - min_z) in the mesh precision (src/solvers/free_space.jl:39)
+    if (mdt == SCB_F32) {
+        const float lo = (float)min_z, hi = (float)max_z;
+        return (double)(2.0f * lo + (hi - lo));
+    }
+    return 2.0 * min_z + (max_z - min_z);
+}
+
+double key_to_double(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int scb_version(void) { return 100; }
+
+int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle** out) {
+    if (!out) return SCB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return SCB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SCB_ERR_NO_DEVICE;
+    if (prop.major != 10) return SCB_ERR_NO_DEVICE;  // sm_100a code only; no fallback path exists
+    if (cudaSetDevice(device) != cudaSuccess) return SCB_ERR_CUDA;
+    scb_handle* h = new scb_handle();
+    h->device = device;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->opt.green_cache = 1;
+    if (opt) h->opt = *opt;
+    if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete h;
+        return SCB_ERR_ALLOC;
+    }
+    *out = h;
+    return SCB_OK;
+}
+
+int scb_destroy(scb_handle* h) {
+    if (!h) return SCB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
+    free_green(h);
+    for (auto& kv : h->twiddles) cudaFree(kv.second);
+    if (h->arena) cudaFree(h->arena);
+    if (h->stage) cudaFree(h->stage);
+    if (h->d_bounds) cudaFree(h->d_bounds);
+    if (h->ev_ready)
+        for (auto& e : h->ev) cudaEventDestroy(e);
+    for (auto& e : h->chunk_ev) cudaEventDestroy(e);
+    delete h;
+    return SCB_OK;
+}
+
+int scb_set_stream(scb_handle* h, void* cuda_stream) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SCB_OK;
+}
+
+int scb_sync(scb_handle* h) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SCB_OK;
+}
+
+const char* scb_last_error(const scb_handle* h) { return h ? h->err.c_str() : "invalid handle"; }
+
+int scb_enable_timing(scb_handle* h, int on) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (on && !h->ev_ready) {
+        for (auto& e : h->ev) SCB_CUDA(h, cudaEventCreate(&e));
+        h->ev_ready = true;
+    }
+    h->timing = on != 0;
+    return SCB_OK;
+}
+
+int scb_get_timing(scb_handle* h, scb_timing* out) {
+    if (!h || !out) return SCB_ERR_INVALID_ARG;
+    if (!h->ev_ready) return fail(h, SCB_ERR_INVALID_ARG, "timing was never enabled");
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    auto el = [&](int a, int b) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 0.f;
+        }
+        return ms;
+    };
+    if (h->t_dep) h->last.deposit_ms = el(0, 1);
+    if (h->t_solve) h->last.solve_ms = el(2, 3);
+    if (h->t_interp) h->last.interpolate_ms = el(4, 5);
+    h->last.green_ms = h->t_green ? el(6, 7) : 0.f;
+    if (h->t_pass)
+        for (int i = 0; i < 5; ++i) h->last.pass_ms[i] = el(8 + i, 9 + i);
+    *out = h->last;
+    return SCB_OK;
+}
+
+int64_t scb_launch_count(const scb_handle* h) { return h ? h->launches : 0; }
+
+int scb_clear(scb_handle* h, void* rho, const int64_t n[3], int mdt) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!rho || !n || !valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_clear");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
+    return SCB_OK;
+}
+
+int scb_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
+                void* rho, int mdt, const int64_t n[3], const double min_bounds[3], const double delta[3], int clear) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !rho || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_deposit");
+    if (np > 0 && (!x || !y || !z || !q)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    tick(h, 0);
+    if (clear) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
+    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, make_geom(n, min_bounds, delta), h->stream));
+    tick(h, 1);
+    h->t_dep = true;
+    if (np > 0) h->launches += 1;
+    return SCB_OK;
+}
+
+int scb_solve(scb_handle* h, const void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+              const double max_bounds[3], const double delta[3], double gamma, int at_cathode) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!min_bounds || !max_bounds) return fail(h, SCB_ERR_INVALID_ARG, "null bounds");
+    double offset[3] = {0.0, 0.0, 0.0};
+    if (at_cathode) {
+        if (!valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad mesh dtype");
+        offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
+    }
+    return solve_dispatch(h, rho, efield, mdt, n, delta, gamma, at_cathode ? 1 : 0, offset);
+}
+
+int scb_solve_freespace(scb_handle* h, const void* rho, void* efield, int mdt, const int64_t n[3],
+                        const double delta[3], double gamma, const double offset[3]) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!offset) return fail(h, SCB_ERR_INVALID_ARG, "null offset");
+    const bool zero = offset[0] == 0.0 && offset[1] == 0.0 && offset[2] == 0.0;
+    return solve_dispatch(h, rho, efield, mdt, n, delta, gamma, zero ? 0 : 2, offset);
+}
+
+int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
+                    const void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                    const double delta[3], void* ex, void* ey, void* ez) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !efield || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_interpolate");
+    if (np > 0 && (!x || !y || !z || !ex || !ey || !ez)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    tick(h, 4);
+    SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, make_geom(n, min_bounds, delta), ex, ey, ez, h->stream));
+    tick(h, 5);
+    h->t_interp = true;
+    if (np > 0) h->launches += 1;
+    return SCB_OK;
+}
+
+int scb_green(scb_handle* h, void* out, const int64_t n2[3], const double delta[3], double gamma, int icomp,
+              const double offset[3], int dt) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!out || !n2 || !delta || !offset || !valid_dt(dt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_green");
+    for (int a = 0; a < 3; ++a)
+        if (n2[a] < 2 || n2[a] > 2 * kMaxFftLen) return fail(h, SCB_ERR_INVALID_ARG, "bad doubled grid size");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    IgfGeom g{};
+    for (int a = 0; a < 3; ++a) {
+        g.isize[a] = (int)n2[a];
+        g.i0[a] = 1;
+        g.cnt[a] = (int)n2[a];
+        g.delta[a] = delta[a];
+        g.offset[a] = offset[a];
+    }
+    g.gamma = gamma;
+    const size_t total = (size_t)n2[0] * n2[1] * n2[2];
+    SCB_TRY(ensure_arena(h, total * 8));
+    double* P = static_cast<double*>(h->arena);
+    SCB_CUDA(h, launch_green_point(P, g, icomp, h->stream));
+    SCB_CUDA(h, launch_green_reference_layout(out, dt == SCB_F64, P, (int)n2[0], (int)n2[1], (int)n2[2], h->stream));
+    h->launches += 2;
+    return SCB_OK;
+}
+
+int scb_bounds(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, double out_min[3],
+               double out_max[3]) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np <= 0) return fail(h, SCB_ERR_INVALID_ARG, "Particle arrays cannot be empty.");
+    if (!x || !y || !z || !out_min || !out_max || !valid_dt(pdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_bounds");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_CUDA(h, launch_bounds(pdt, np, x, y, z, reinterpret_cast<double*>(h->d_bounds), h->stream));
+    h->launches += 2;
+    unsigned long long host[6];
+    SCB_CUDA(h, cudaMemcpyAsync(host, h->d_bounds, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < 3; ++a) {
+        out_min[a] = key_to_double(host[a]);
+        out_max[a] = key_to_double(host[3 + a]);
+    }
+    return SCB_OK;
+}
+
+int scb_cell_index(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, int mdt,
+                   const double min_bounds[3], const double delta[3], int64_t* ix, int64_t* iy, int64_t* iz) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_cell_index");
+    if (np > 0 && (!x || !y || !z || !ix || !iy || !iz)) return fail(h, SCB_ERR_INVALID_ARG, "null array");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n1[3] = {2, 2, 2};
+    SCB_CUDA(h, launch_cell_index(pdt, mdt, np, x, y, z, make_geom(n1, min_bounds, delta), (long long*)ix,
+                                  (long long*)iy, (long long*)iz, h->stream));
+    if (np > 0) h->launches += 1;
+    return SCB_OK;
+}
+
+int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
+             void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+             const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* ex, void* ey,
+             void* ez) {
+    SCB_TRY(scb_deposit(h, np, x, y, z, q, pdt, rho, mdt, n, min_bounds, delta, 1));
+    SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    return scb_interpolate(h, np, x, y, z, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
+}
+
+int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
+                  void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                  const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
+                  void* eyh, void* ezh) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np <= 0 || !xh || !yh || !zh || !qh || !exh || !eyh || !ezh || !rho || !efield || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_step_host");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    const size_t es = dt_size(pdt);
+    const size_t arr = ((size_t)np * es + 255) / 256 * 256;
+    if (h->stage_bytes < 7 * arr) {
+        if (h->stage) {
+            SCB_CUDA(h, cudaDeviceSynchronize());
+            cudaFree(h->stage);
+            h->stage = nullptr;
+            h->stage_bytes = 0;
+        }
+        if (cudaMalloc(&h->stage, 7 * arr) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(h, SCB_ERR_ALLOC, "particle staging allocation failed");
+        }
+        h->stage_bytes = 7 * arr;
+    }
+    if (!h->copy_stream) SCB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    char* d[7];
+    for (int i = 0; i < 7; ++i) d[i] = static_cast<char*>(h->stage) + i * arr;
+    const void* src[4] = {xh, yh, zh, qh};
+    void* dsth[3] = {exh, eyh, ezh};
+
+    const int64_t chunk = 1 << 22;
+    const int nchunk = (int)((np + chunk - 1) / chunk);
+    while ((int)h->chunk_ev.size() < 2 * nchunk + 2) {
+        cudaEvent_t e;
+        SCB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunk_ev.push_back(e);
+    }
+    const Geom3 g = make_geom(n, min_bounds, delta);
+    // make the copy stream wait for whatever the caller queued before this call
+    SCB_CUDA(h, cudaEventRecord(h->chunk_ev[2 * nchunk], h->stream));
+    SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * nchunk], 0));
+    SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t o = (int64_t)c * chunk, m = (np - o) < chunk ? (np - o) : chunk;
+        for (int a = 0; a < 4; ++a)
+            SCB_CUDA(h, cudaMemcpyAsync(d[a] + o * es, (const char*)src[a] + o * es, m * es, cudaMemcpyHostToDevice, h->copy_stream));
+        SCB_CUDA(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+        SCB_CUDA(h, launch_deposit(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, d[3] + o * es, rho, g, h->stream));
+        h->launches += 1;
+    }
+    SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t o = (int64_t)c * chunk, m = (np - o) < chunk ? (np - o) : chunk;
+        SCB_CUDA(h, launch_interpolate(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, efield, g, d[4] + o * es,
+                                       d[5] + o * es, d[6] + o * es, h->stream));
+        h->launches += 1;
+        SCB_CUDA(h, cudaEventRecord(h->chunk_ev[nchunk + c], h->stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[nchunk + c], 0));
+        for (int a = 0; a < 3; ++a)
+            SCB_CUDA(h, cudaMemcpyAsync((char*)dsth[a] + o * es, d[4 + a] + o * es, m * es, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    SCB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SCB_OK;
+}
+
+int scb_drop_green_cache(scb_handle* h) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    free_green(h);
+    return SCB_OK;
+}
+
+int64_t scb_workspace_bytes(const scb_handle* h) {
+    if (!h) return 0;
+    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes;
+    for (auto& e : h->green) b += (int64_t)e.bytes;
+    return b;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// parity hooks for the individual passes (include/spacecharge_b200_debug.h)
+#include "../../include/spacecharge_b200_debug.h"
+
+namespace {
+
+template <typename T>
+int debug_lines(scb_handle* h, int N, int dir, const void* in, void* out, int n_in, int n_out, int ninner,
+                int64_t in_sline, int64_t in_souter, int64_t out_sline, int64_t out_souter, int nouter, double scale) {
+    const cx_t<T>* tw;
+    SCB_TRY(get_twiddles<T>(h, N, &tw));
+    LinesParams<T> p{};
+    p.in = static_cast<const cx_t<T>*>(in);
+    p.out = static_cast<cx_t<T>*>(out);
+    p.tw = tw;
+    p.n_in = n_in;
+    p.n_out = n_out;
+    p.ninner = ninner;
+    p.in_sline = in_sline;
+    p.in_souter = in_souter;
+    p.out_sline = out_sline;
+    p.out_souter = out_souter;
+    p.scale = (T)scale;
+    SCB_CUDA(h, launch_lines<T>(N, dir, p, nouter, 1, h->stream));
+    h->launches += 1;
+    return SCB_OK;
+}
+
+template <typename T>
+int debug_x(scb_handle* h, bool r2c, int N, const void* in, void* out, int64_t nlines, int64_t real_sline, int n_real,
+            int PX, double scale) {
+    const cx_t<T>* tw;
+    SCB_TRY(get_twiddles<T>(h, N, &tw));
+    XParams<T> p{};
+    p.in = in;
+    p.out = out;
+    p.tw = tw;
+    p.nlines = nlines;
+    p.real_sline = real_sline;
+    p.n_real = n_real;
+    p.PX = PX;
+    p.scale = (T)scale;
+    if (r2c) SCB_CUDA(h, launch_x_r2c<T>(N, p, 1, h->stream));
+    else SCB_CUDA(h, launch_x_c2r<T>(N, p, 1, h->stream));
+    h->launches += 1;
+    return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scb_debug_fft_lines(scb_handle* h, int dt, int N, int dir, const void* in, void* out, int n_in, int n_out,
+                        int ninner, int64_t in_sline, int64_t in_souter, int64_t out_sline, int64_t out_souter,
+                        int nouter, double scale) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!in || !out || !valid_dt(dt) || !fft_len_supported(N) || nouter < 1 || ninner < 1)
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_debug_fft_lines");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    if (dt == SCB_F64)
+        return debug_lines<double>(h, N, dir, in, out, n_in, n_out, ninner, in_sline, in_souter, out_sline, out_souter, nouter, scale);
+    return debug_lines<float>(h, N, dir, in, out, n_in, n_out, ninner, in_sline, in_souter, out_sline, out_souter, nouter, scale);
+}
+
+int scb_debug_fft_x_r2c(scb_handle* h, int dt, int N, const void* in, void* out, int64_t nlines, int64_t real_sline,
+                        int n_real, int PX) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!in || !out || !valid_dt(dt) || !fft_len_supported(N) || nlines < 1 || PX < N / 2 + 1)
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_debug_fft_x_r2c");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    if (dt == SCB_F64) return debug_x<double>(h, true, N, in, out, nlines, real_sline, n_real, PX, 1.0);
+    return debug_x<float>(h, true, N, in, out, nlines, real_sline, n_real, PX, 1.0);
+}
+
+int scb_debug_fft_x_c2r(scb_handle* h, int dt, int N, const void* in, void* out, int64_t nlines, int64_t real_sline,
+                        int n_real, int PX, double scale) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!in || !out || !valid_dt(dt) || !fft_len_supported(N) || nlines < 1 || PX < N / 2 + 1)
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_debug_fft_x_c2r");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    if (dt == SCB_F64) return debug_x<double>(h, false, N, in, out, nlines, real_sline, n_real, PX, scale);
+    return debug_x<float>(h, false, N, in, out, nlines, real_sline, n_real, PX, scale);
+}
+
+}  // extern "C"

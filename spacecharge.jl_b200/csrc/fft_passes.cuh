@@ -1,0 +1,287 @@
+// fft_passes.cuh -- the five pass groups of the pruned FFT convolution and the
+// generic passes used to build the Green-function spectrum.
+//
+// Data layout of every complex intermediate: x (kx) fastest with pitch PX (a multiple of 8,
+// >= Lx/2+1), then y, then z.  Only kx in [0, Lx/2] is kept (real input => Hermitian spectrum).
+//
+//   F1  x_r2c      rho (nx,ny,nz) real  -> A [kx][y ][z ]   zero-pad nx->Lx fused into the load,
+//                                                          two real lines per complex transform
+//   F2  lines<-1>  A                    -> B [kx][ky][z ]   zero-pad ny->Ly fused into the load
+//   Z   z_fused    B                    -> C_c[kx][ky][z ]  pad nz->Lz, forward, x Green_c
+//                                                          (+ mirrored spectrum x image Green_c),
+//                                                          inverse, keep first nz; c = 0,1,2
+//   B2  lines<+1>  C_c                  -> D_c[kx][y ][z ]  inverse along y, keep first ny
+//   B3  x_c2r      D_c                  -> E_c (nx,ny,nz)   inverse along x, keep first nx,
+//                                                          x FPEI/(Lx Ly Lz) fused into the store
+//
+// replaces: src/solvers/free_space.jl:68-99 (fill!, embed, 7 in-place C2C FFTs, multiply,
+// scale, extract) of the reference.
+#pragma once
+#include "fft_engine.cuh"
+
+namespace scb {
+
+// threads that advance in lockstep along the contiguous axis in the strided passes
+__host__ __device__ constexpr int tx_for(int N) {
+    return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? 8 : N == 128 ? 16 : 32;
+}
+// line pairs per CTA in the x passes
+__host__ __device__ constexpr int lp_for(int N) { return (N / 8) >= 256 ? 1 : 256 / (N / 8); }
+
+enum GreenKind : int { GREEN_FREE = 0, GREEN_CATHODE = 1, GREEN_FULL = 2 };
+
+// ------------------------------------------------------------------------------------------
+// generic strided complex pass
+template <typename T>
+struct LinesParams {
+    const cx_t<T>* in;
+    cx_t<T>* out;
+    const cx_t<T>* tw;
+    int n_in, n_out;    // positions >= n_in read as zero; bins >= n_out are not stored
+    int ninner;         // valid elements along the contiguous axis
+    long long in_sline, in_souter, out_sline, out_souter;
+    long long in_scomp, out_scomp;  // blockIdx.z selects the field component
+    T scale;
+};
+
+template <typename T, int N, int DIR>
+__global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams<T> p) {
+    using C = cx_t<T>;
+    constexpr int TX = tx_for(N);
+    constexpr int TPL = N / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tx = threadIdx.x, j = threadIdx.y;
+    const int kx = blockIdx.x * TX + tx;
+    const bool valid = kx < p.ninner;
+    LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
+
+    C v[8];
+    const C* src = p.in + (long long)blockIdx.z * p.in_scomp + (long long)blockIdx.y * p.in_souter + kx;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = j + q * TPL;
+        v[q] = (valid && pos < p.n_in) ? ld_stream(src + pos * p.in_sline) : cmake<C>(0, 0);
+    }
+    fft_line<T, N, DIR>(v, lay, j, p.tw);
+    C* dst = p.out + (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = j + q * TPL;
+        if (valid && pos < p.n_out) dst[pos * p.out_sline] = cscale(v[q], p.scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused z pass
+template <typename T>
+struct ZParams {
+    const cx_t<T>* in;      // B  [kx + PX*(ky + Ly*z)]
+    cx_t<T>* out;           // C_c at out + c*out_scomp, same layout
+    const cx_t<T>* tw;
+    long long out_scomp;
+    int nz;                 // valid z planes in and out
+    int ninner, PX, Ly;
+    // GREEN_FREE / GREEN_CATHODE: compressed real spectrum S_c[kx + PXg*(ky' + (Ly/2+1)*kz')],
+    // Green_c = i * sign * S_c with ky' = min(ky, Ly-ky), kz' = min(kz, Lz-kz)
+    const T* S;
+    long long S_scomp;
+    // GREEN_CATHODE: image spectrum H_c, GREEN_FULL: G_c; complex [kx + PX*(ky + Ly*kz)]
+    const cx_t<T>* H;
+    long long H_scomp;
+};
+
+template <typename T, int N, int KIND>
+__global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_z_fused(const ZParams<T> p) {
+    using C = cx_t<T>;
+    constexpr int TX = tx_for(N);
+    constexpr int TPL = N / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tx = threadIdx.x, j = threadIdx.y;
+    const int kx = blockIdx.x * TX + tx;
+    const int ky = blockIdx.y;
+    const bool valid = kx < p.ninner;
+    LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
+    const long long plane = (long long)p.PX * p.Ly;
+
+    C spec[8];
+    {
+        const C* src = p.in + (long long)ky * p.PX + kx;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int pos = j + q * TPL;
+            spec[q] = (valid && pos < p.nz) ? ld_stream(src + pos * plane) : cmake<C>(0, 0);
+        }
+    }
+    fft_line<T, N, -1>(spec, lay, j, p.tw);
+
+    // second buffer keeps the forward spectrum so that bin (-kz) can be read by other threads
+    LayoutRows<C, TX> laym(reinterpret_cast<C*>(smem_raw + LayoutRows<C, TX>::bytes(N)), tx);
+    if constexpr (KIND == GREEN_CATHODE) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) laym.st(j + q * TPL, spec[q]);
+        __syncthreads();
+    }
+
+    const int Lyh = p.Ly / 2;
+    const int kyf = ky <= Lyh ? ky : p.Ly - ky;  // folded ky
+
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+        C w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int kz = j + q * TPL;
+            C acc = cmake<C>(0, 0);
+            if (valid) {
+                if constexpr (KIND == GREEN_FREE || KIND == GREEN_CATHODE) {
+                    const int kzf = kz <= N / 2 ? kz : N - kz;
+                    T s = __ldg(p.S + c * p.S_scomp + kx + (long long)p.PX * (kyf + (long long)(Lyh + 1) * kzf));
+                    if ((c == 1 && ky > Lyh) || (c == 2 && kz > N / 2)) s = -s;
+                    // (a + ib) * (i s) = s * (-b + i a)
+                    acc = cmake<C>(-spec[q].y * s, spec[q].x * s);
+                }
+                if constexpr (KIND == GREEN_CATHODE) {
+                    const C h = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Ly * kz));
+                    const C m = laym.ld((N - kz) & (N - 1));
+                    acc = cadd(acc, cmul(m, h));
+                }
+                if constexpr (KIND == GREEN_FULL) {
+                    const C g = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Ly * kz));
+                    acc = cmul(spec[q], g);
+                }
+            }
+            w[q] = acc;
+        }
+        fft_line<T, N, +1>(w, lay, j, p.tw);
+        C* dst = p.out + c * p.out_scomp + (long long)ky * p.PX + kx;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int pos = j + q * TPL;
+            if (valid && pos < p.nz) dst[pos * plane] = w[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x passes: real <-> half-complex along the contiguous axis, two real lines per transform
+template <typename T>
+struct XParams {
+    const void* in;
+    void* out;
+    const cx_t<T>* tw;
+    long long nlines;       // real lines (ny*nz), complex lines on the other side match 1:1
+    long long real_sline;   // elements between consecutive real lines
+    int n_real;             // valid reals per line (nx): zero beyond on load, not stored on store
+    int PX;                 // pitch of the complex lines
+    long long real_scomp, cplx_scomp;  // blockIdx.y selects the field component
+    T scale;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> p) {
+    using C = cx_t<T>;
+    constexpr int TPL = N / 8;
+    constexpr int ROW = LayoutLine<C>::row(N);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int j = threadIdx.x, lp = threadIdx.y;
+    const long long pair = (long long)blockIdx.x * lp_for(N) + lp;
+    const long long la = 2 * pair, lb = 2 * pair + 1;
+    const bool va = la < p.nlines, vb = lb < p.nlines;
+    LayoutLine<C> lay(reinterpret_cast<C*>(smem_raw) + (size_t)lp * ROW);
+    const T* ra = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + la * p.real_sline;
+    const T* rb = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + lb * p.real_sline;
+
+    C v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = j + q * TPL;
+        const bool in_range = pos < p.n_real;
+        const T a = (va && in_range) ? ld_stream(ra + pos) : (T)0;
+        const T b = (vb && in_range) ? ld_stream(rb + pos) : (T)0;
+        v[q] = cmake<C>(a, b);
+    }
+    fft_line<T, N, -1>(v, lay, j, p.tw);
+
+    // split the two interleaved Hermitian spectra: needs bins k and N-k
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lay.st(j + q * TPL, v[q]);
+    __syncthreads();
+    C* oa = static_cast<C*>(p.out) + (long long)blockIdx.y * p.cplx_scomp + la * p.PX;
+    C* ob = static_cast<C*>(p.out) + (long long)blockIdx.y * p.cplx_scomp + lb * p.PX;
+    const T half = (T)0.5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = j + q * TPL;
+        const C zk = v[q];
+        const C zm = lay.ld((N - k) & (N - 1));
+        const C A = cmake<C>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+        const C B = cmake<C>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
+        if (va) oa[k] = A;
+        if (vb) ob[k] = B;
+    }
+    if (j == 0) {  // Nyquist bin N/2 lives in v[4] of thread 0
+        if (va) oa[N / 2] = cmake<C>(v[4].x, 0);
+        if (vb) ob[N / 2] = cmake<C>(v[4].y, 0);
+    }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> p) {
+    using C = cx_t<T>;
+    constexpr int TPL = N / 8;
+    constexpr int ROW = LayoutLine<C>::row(N);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int j = threadIdx.x, lp = threadIdx.y;
+    const long long pair = (long long)blockIdx.x * lp_for(N) + lp;
+    const long long la = 2 * pair, lb = 2 * pair + 1;
+    const bool va = la < p.nlines, vb = lb < p.nlines;
+    LayoutLine<C> lay(reinterpret_cast<C*>(smem_raw) + (size_t)lp * ROW);
+    const C* ia = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + la * p.PX;
+    const C* ib = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + lb * p.PX;
+
+    // Z[k] = A[k] + i B[k],  Z[N-k] = conj(A[k]) + i conj(B[k])
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = j + q * TPL;
+        const C a = va ? ld_stream(ia + k) : cmake<C>(0, 0);
+        const C b = vb ? ld_stream(ib + k) : cmake<C>(0, 0);
+        if (k == 0) {
+            lay.st(0, cmake<C>(a.x, b.x));
+        } else {
+            lay.st(k, cmake<C>(a.x - b.y, a.y + b.x));
+            lay.st(N - k, cmake<C>(a.x + b.y, b.x - a.y));
+        }
+    }
+    if (j == 0) {
+        const C a = va ? ld_stream(ia + N / 2) : cmake<C>(0, 0);
+        const C b = vb ? ld_stream(ib + N / 2) : cmake<C>(0, 0);
+        lay.st(N / 2, cmake<C>(a.x, b.x));
+    }
+    __syncthreads();
+    C v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = lay.ld(j + q * TPL);
+    fft_line<T, N, +1>(v, lay, j, p.tw);
+
+    T* oa = static_cast<T*>(p.out) + (long long)blockIdx.y * p.real_scomp + la * p.real_sline;
+    T* ob = static_cast<T*>(p.out) + (long long)blockIdx.y * p.real_scomp + lb * p.real_sline;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = j + q * TPL;
+        if (pos < p.n_real) {
+            if (va) oa[pos] = v[q].x * p.scale;
+            if (vb) ob[pos] = v[q].y * p.scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers (defined per precision in fft_passes_f32.cu / fft_passes_f64.cu)
+template <typename T> cudaError_t launch_lines(int N, int dir, const LinesParams<T>& p, int nouter, int ncomp, cudaStream_t s);
+template <typename T> cudaError_t launch_z_fused(int N, int kind, const ZParams<T>& p, cudaStream_t s);
+template <typename T> cudaError_t launch_x_r2c(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
+template <typename T> cudaError_t launch_x_c2r(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
+bool fft_len_supported(int N);
+
+}  // namespace scb

@@ -1,0 +1,164 @@
+// green.cu -- integrated Green function (IGF) kernels, always evaluated in double.
+//
+// replaces: src/green_functions.jl:35-38 (field_green_function), :69-101 (get_green_kernel!),
+// :103-112 (apply_8point_differencing!) and :41-67 (get_green_function!) of the reference.
+//
+// The reference fills the whole doubled (2n)^3 array point-wise and differences it, three times
+// per solve.  Here the point-wise values are produced only on the corner ranges that are needed
+// (an octant when the offset along an axis is zero: the IGF is odd along its own axis and even
+// along the other two), the 8-point differencing is fused into the kernel that places the IGF
+// into the zero-padded, wrap-around array handed to the FFT passes, and the resulting spectrum is
+// cached per geometry by the caller (api.cu).
+//
+// Compiled with -fmad=false so that u = (i-1)*dx + umin and the closed form round exactly like
+// the reference's un-contracted Julia arithmetic.
+#include "kernels.h"
+
+namespace scb {
+
+// src/green_functions.jl:35-38
+__device__ __forceinline__ double field_green(double x, double y, double z) {
+    const double r = sqrt(x * x + y * y + z * z);
+    return x * atan((y * z) / (r * x)) - z * log(r + y) + y * log((r - z) / (r + z)) / 2.0;
+}
+
+// Point-wise values P[mx + cx*(my + cy*mz)] for corner m <-> reference 1-based index i = i0 + m.
+// src/green_functions.jl:69-101
+__global__ void k_green_point(double* __restrict__ P, IgfGeom g, int icomp) {
+    const long long total = (long long)g.cnt[0] * g.cnt[1] * g.cnt[2];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int mx = (int)(idx % g.cnt[0]);
+    const int my = (int)((idx / g.cnt[0]) % g.cnt[1]);
+    const int mz = (int)(idx / ((long long)g.cnt[0] * g.cnt[1]));
+    const double dx = g.delta[0], dy = g.delta[1], dz = g.delta[2] * g.gamma;
+    const double factor = (icomp == 1 || icomp == 2) ? g.gamma / (dx * dy * dz) : 1.0 / (dx * dy * dz);
+    const double umin = (double)(1 - g.isize[0]) * dx / 2.0 + g.offset[0];
+    const double vmin = (double)(1 - g.isize[1]) * dy / 2.0 + g.offset[1];
+    const double wmin = (double)(1 - g.isize[2]) * dz / 2.0 + g.offset[2] * g.gamma;
+    const double u = (double)(g.i0[0] + mx - 1) * dx + umin;
+    const double v = (double)(g.i0[1] + my - 1) * dy + vmin;
+    const double w = (double)(g.i0[2] + mz - 1) * dz + wmin;
+    double gv;
+    if (icomp == 1) gv = field_green(u, v, w) * factor;
+    else if (icomp == 2) gv = field_green(v, w, u) * factor;
+    else if (icomp == 3) gv = field_green(w, u, v) * factor;
+    else gv = 0.0;
+    P[idx] = gv;
+}
+
+// src/green_functions.jl:103-112, same left-to-right order
+__device__ __forceinline__ double diff8(const double* __restrict__ P, int cx, int cy, int i, int j, int k) {
+    auto at = [&](int a, int b, int c) { return __ldg(P + a + (long long)cx * (b + (long long)cy * c)); };
+    return at(i + 1, j + 1, k + 1) - at(i, j + 1, k + 1) - at(i + 1, j, k + 1) - at(i + 1, j + 1, k) -
+           at(i, j, k) + at(i, j, k + 1) + at(i, j + 1, k) + at(i + 1, j, k);
+}
+
+// Parity hook (scb_green): the reference's own array -- differenced block plus raw last planes.
+template <typename TO>
+__global__ void k_green_reference_layout(TO* __restrict__ out, const double* __restrict__ P, int sx, int sy, int sz) {
+    const long long total = (long long)sx * sy * sz;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int i = (int)(idx % sx), j = (int)((idx / sx) % sy), k = (int)(idx / ((long long)sx * sy));
+    double v;
+    if (i < sx - 1 && j < sy - 1 && k < sz - 1) v = diff8(P, sx, sy, i, j, k);
+    else v = P[idx];
+    out[idx] = (TO)v;
+}
+
+// Differencing fused with placement into the padded real array g[X + Lx*(Y + Ly*Z)].
+// axis modes: conv = wrap-around placement of displacement d at index d mod L;
+//             corr = displacement d at index d + (n-1) (image charge along z).
+__global__ void k_green_place(double* __restrict__ gout, const double* __restrict__ P, IgfGeom g, int icomp, double sign_all) {
+    const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int X[3];
+    X[0] = (int)(idx % g.L[0]);
+    X[1] = (int)((idx / g.L[0]) % g.L[1]);
+    X[2] = (int)(idx / ((long long)g.L[0] * g.L[1]));
+    int m0[3];
+    double sgn = sign_all;
+    bool zero = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int n = g.n[a], L = g.L[a];
+        int d;
+        if (g.corr[a]) {
+            if (X[a] <= 2 * n - 2) d = X[a] - (n - 1);
+            else { zero = true; d = 0; }
+        } else {
+            if (X[a] <= n - 1) d = X[a];
+            else if (X[a] >= L - (n - 1)) d = X[a] - L;
+            else { zero = true; d = 0; }
+        }
+        if (g.sym[a]) {           // octant stored: corners i0 = n (1-based) .. 2n
+            if (d < 0) { d = -d; if (a == icomp - 1) sgn = -sgn; }
+            m0[a] = d;
+        } else {                  // full range stored: corners 1 .. 2n
+            m0[a] = d + n - 1;
+        }
+    }
+    gout[idx] = zero ? 0.0 : sgn * diff8(P, g.cnt[0], g.cnt[1], m0[0], m0[1], m0[2]);
+}
+
+// Spectrum -> cached forms.
+// free space: Green_c = i*S_c, S_c real, kept for kx<=Lx/2, ky<=Ly/2, kz<=Lz/2
+template <typename T>
+__global__ void k_green_compress_free(T* __restrict__ S, const double2* __restrict__ spec, int ninner, int PX, int Ly, int Lz) {
+    const int Lyh = Ly / 2 + 1, Lzh = Lz / 2 + 1;
+    const long long total = (long long)PX * Lyh * Lzh;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int kx = (int)(idx % PX), ky = (int)((idx / PX) % Lyh), kz = (int)(idx / ((long long)PX * Lyh));
+    T v = (T)0;
+    if (kx < ninner) v = (T)spec[kx + (long long)PX * (ky + (long long)Ly * kz)].y;
+    S[idx] = v;
+}
+
+template <typename T>
+__global__ void k_green_convert_full(cx_t<T>* __restrict__ G, const double2* __restrict__ spec, int ninner, int PX, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int kx = (int)(idx % PX);
+    double2 v = kx < ninner ? spec[idx] : make_double2(0.0, 0.0);
+    G[idx] = cmake<cx_t<T>>((T)v.x, (T)v.y);
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+static inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStream_t s) {
+    const long long total = (long long)g.cnt[0] * g.cnt[1] * g.cnt[2];
+    k_green_point<<<blocks_for(total, 256), 256, 0, s>>>(P, g, icomp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s) {
+    const long long total = (long long)sx * sy * sz;
+    if (dt_f64) k_green_reference_layout<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)out, P, sx, sy, sz);
+    else k_green_reference_layout<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)out, P, sx, sy, sz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_place(double* gout, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s) {
+    const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
+    k_green_place<<<blocks_for(total, 256), 256, 0, s>>>(gout, P, g, icomp, sign_all);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Ly, int Lz, cudaStream_t s) {
+    const long long total = (long long)PX * (Ly / 2 + 1) * (Lz / 2 + 1);
+    if (dt_f64) k_green_compress_free<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)S, spec, ninner, PX, Ly, Lz);
+    else k_green_compress_free<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, ninner, PX, Ly, Lz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, int ninner, int PX, long long total, cudaStream_t s) {
+    if (dt_f64) k_green_convert_full<double><<<blocks_for(total, 256), 256, 0, s>>>((double2*)G, spec, ninner, PX, total);
+    else k_green_convert_full<float><<<blocks_for(total, 256), 256, 0, s>>>((float2*)G, spec, ninner, PX, total);
+    return cudaGetLastError();
+}
+
+}  // namespace scb

@@ -1,0 +1,44 @@
+// kernels.h -- internal interface between the kernel translation units and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace scb {
+
+struct IgfGeom {
+    int n[3];       // grid size
+    int L[3];       // padded FFT length per axis (power of two >= 2n)
+    int isize[3];   // the reference's doubled array size 2n (src/green_functions.jl:71)
+    int i0[3];      // first 1-based reference index held in the point-wise table
+    int cnt[3];     // corners held per axis
+    int sym[3];     // 1: octant stored (offset == 0 along the axis), mirrored with parity
+    int corr[3];    // 1: correlation placement (image charge), 0: wrap-around convolution
+    double delta[3];
+    double gamma;
+    double offset[3];
+};
+
+struct Geom3 {
+    double lo[3];
+    double delta[3];
+    int n[3];
+};
+
+// green.cu
+cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStream_t s);
+cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s);
+cudaError_t launch_green_place(double* gout, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s);
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Ly, int Lz, cudaStream_t s);
+cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, int ninner, int PX, long long total, cudaStream_t s);
+
+// particles.cu  (pdt/mdt: 0 = f32, 1 = f64)
+cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                           const void* q, void* rho, const Geom3& g, cudaStream_t s);
+cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
+cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                              const Geom3& g, long long* ix, long long* iy, long long* iz, cudaStream_t s);
+// partial[0..2] = min, partial[3..5] = max as doubles; must be initialised by the launcher
+cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z,
+                          double* out6, cudaStream_t s);
+
+}  // namespace scb

@@ -1,0 +1,212 @@
+// particles.cu -- the particle passes: cloud-in-cell deposit, trilinear gather, extrema, indices.
+//
+// replaces: src/deposition.jl:28-86 (deposit_particle!), :106-158 (deposit_kernel!/deposit_gpu!)
+//           src/interpolation.jl:17-86 (interpolate_kernel!), src/mesh.jl:120-122 (extrema)
+//
+// Arithmetic follows the reference exactly: normalised
+// coordinate with a true IEEE division in promote(P, T), floor, fraction, left-to-right weight
+// products.  Compiled with -fmad=false (Julia does not contract a*b+c).  The only deviation is
+// the clamp of the cell index to [0, n-2]: identical for in-range particles, and it removes the
+// out-of-bounds write the reference performs for Float32 auto-bounds meshes.
+#include "kernels.h"
+
+namespace scb {
+
+template <typename P, typename T> struct promote { using type = double; };
+template <> struct promote<float, float> { using type = float; };
+
+template <typename W> struct CellW {
+    int i[3];
+    W f[3];
+};
+
+template <typename W>
+__device__ __forceinline__ void locate(W px, W py, W pz, const Geom3& g, CellW<W>& c) {
+    const W p[3] = {px, py, pz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const W t = (p[a] - (W)g.lo[a]) / (W)g.delta[a];
+        W fl = floor(t);
+        fl = fmin(fmax(fl, (W)0), (W)(g.n[a] - 2));
+        c.i[a] = (int)fl;
+        c.f[a] = t - fl;
+    }
+}
+
+// ---- deposit: one thread per particle, eight reductions into rho --------------------------
+template <typename P, typename T>
+__global__ void __launch_bounds__(256) k_deposit(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                  const P* __restrict__ z, const P* __restrict__ q,
+                                                  T* __restrict__ rho, const Geom3 g) {
+    using W = typename promote<P, T>::type;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
+        CellW<W> c;
+        locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+        const W charge = (W)ld_stream(q + i);
+        const W wx0 = (W)1 - c.f[0], wx1 = c.f[0];
+        const W wy0 = (W)1 - c.f[1], wy1 = c.f[1];
+        const W wz0 = (W)1 - c.f[2], wz1 = c.f[2];
+        T* r = rho + c.i[0] + (long long)g.n[0] * (c.i[1] + (long long)g.n[1] * c.i[2]);
+        const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+        // order of src/deposition.jl:67-74
+        atomicAdd(r, (T)(charge * wx0 * wy0 * wz0));
+        atomicAdd(r + 1, (T)(charge * wx1 * wy0 * wz0));
+        atomicAdd(r + sy, (T)(charge * wx0 * wy1 * wz0));
+        atomicAdd(r + sy + 1, (T)(charge * wx1 * wy1 * wz0));
+        atomicAdd(r + sz, (T)(charge * wx0 * wy0 * wz1));
+        atomicAdd(r + sz + 1, (T)(charge * wx1 * wy0 * wz1));
+        atomicAdd(r + sz + sy, (T)(charge * wx0 * wy1 * wz1));
+        atomicAdd(r + sz + sy + 1, (T)(charge * wx1 * wy1 * wz1));
+    }
+}
+
+// ---- interpolate: one thread per particle, 24 gathers --------------------------------------
+template <typename P, typename T>
+__global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                      const P* __restrict__ z, const T* __restrict__ e,
+                                                      const Geom3 g, P* __restrict__ ex, P* __restrict__ ey,
+                                                      P* __restrict__ ez) {
+    using W = typename promote<P, T>::type;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1], sc = sz * g.n[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
+        CellW<W> c;
+        locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+        const W dx = c.f[0], dy = c.f[1], dz = c.f[2];
+        const W one = (W)1;
+        // src/interpolation.jl:46-53
+        const W w000 = (one - dx) * (one - dy) * (one - dz);
+        const W w100 = dx * (one - dy) * (one - dz);
+        const W w010 = (one - dx) * dy * (one - dz);
+        const W w110 = dx * dy * (one - dz);
+        const W w001 = (one - dx) * (one - dy) * dz;
+        const W w101 = dx * (one - dy) * dz;
+        const W w011 = (one - dx) * dy * dz;
+        const W w111 = dx * dy * dz;
+        const T* b = e + c.i[0] + sy * c.i[1] + sz * c.i[2];
+        W out[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T* bk = b + k * sc;
+            // src/interpolation.jl:56-85, left-to-right sum
+            out[k] = (W)__ldg(bk) * w000 + (W)__ldg(bk + 1) * w100 + (W)__ldg(bk + sy) * w010 +
+                     (W)__ldg(bk + sy + 1) * w110 + (W)__ldg(bk + sz) * w001 + (W)__ldg(bk + sz + 1) * w101 +
+                     (W)__ldg(bk + sz + sy) * w011 + (W)__ldg(bk + sz + sy + 1) * w111;
+        }
+        st_stream(ex + i, (P)out[0]);
+        st_stream(ey + i, (P)out[1]);
+        st_stream(ez + i, (P)out[2]);
+    }
+}
+
+// ---- parity hook: unclamped cell indices ----------------------------------------------------
+template <typename P, typename T>
+__global__ void k_cell_index(long long np, const P* __restrict__ x, const P* __restrict__ y, const P* __restrict__ z,
+                             const Geom3 g, long long* __restrict__ ix, long long* __restrict__ iy,
+                             long long* __restrict__ iz) {
+    using W = typename promote<P, T>::type;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    ix[i] = (long long)floor(((W)x[i] - (W)g.lo[0]) / (W)g.delta[0]);
+    iy[i] = (long long)floor(((W)y[i] - (W)g.lo[1]) / (W)g.delta[1]);
+    iz[i] = (long long)floor(((W)z[i] - (W)g.lo[2]) / (W)g.delta[2]);
+}
+
+// ---- extrema -------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void k_bounds_init(unsigned long long* out6) {
+    if (threadIdx.x < 3) out6[threadIdx.x] = ~0ull;
+    else if (threadIdx.x < 6) out6[threadIdx.x] = 0ull;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) k_bounds(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                 const P* __restrict__ z, unsigned long long* __restrict__ out6) {
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
+        const double p[3] = {(double)x[i], (double)y[i], (double)z[i]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], p[a]); hi[a] = fmax(hi[a], p[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (lo[a] <= hi[a]) {
+                atomicMin(out6 + a, order_key(lo[a]));
+                atomicMax(out6 + 3 + a, order_key(hi[a]));
+            }
+        }
+    }
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+static inline unsigned particle_grid(long long np, int bs, int per_sm) {
+    long long want = (np + bs - 1) / bs;
+    long long cap = 148LL * per_sm;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+#define SCB_DISPATCH_PT(CALL)                                                  \
+    if (pdt == 0 && mdt == 0) { CALL(float, float) }                           \
+    else if (pdt == 0 && mdt == 1) { CALL(float, double) }                     \
+    else if (pdt == 1 && mdt == 0) { CALL(double, float) }                     \
+    else { CALL(double, double) }
+
+cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                           const void* q, void* rho, const Geom3& g, cudaStream_t s) {
+    if (np <= 0) return cudaSuccess;
+    const unsigned grid = particle_grid(np, 256, 64);
+#define CALL(P, T) k_deposit<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
+    SCB_DISPATCH_PT(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s) {
+    if (np <= 0) return cudaSuccess;
+    const unsigned grid = particle_grid(np, 256, 64);
+#define CALL(P, T) k_interpolate<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez);
+    SCB_DISPATCH_PT(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                              const Geom3& g, long long* ix, long long* iy, long long* iz, cudaStream_t s) {
+    if (np <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((np + 255) / 256);
+#define CALL(P, T) k_cell_index<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, g, ix, iy, iz);
+    SCB_DISPATCH_PT(CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z, double* out6,
+                          cudaStream_t s) {
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(out6);
+    k_bounds_init<<<1, 32, 0, s>>>(o);
+    if (np > 0) {
+        const unsigned grid = particle_grid(np, 256, 8);
+        if (pdt == 0) k_bounds<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, o);
+        else k_bounds<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, o);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace scb

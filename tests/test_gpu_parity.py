@@ -1,0 +1,283 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.
+
+Tolerances (BASELINE.md section 4 / SURVEY.md 8c): particle->cell indices bit-exact; rho and every
+E component max|a-b|/max|b| <= 1e-10 in Float64; Float32 runs <= 1e-5 against the Float64 oracle
+(the reference's own Float32 solve is only good to ~1e-4).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-10
+TOL32 = 1e-5
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def check(record, name, a, b, tol):
+    e = rel(a, b)
+    record(name, e, tol)
+    assert e < tol, (name, e, tol)
+
+
+def gaussian(n, seed, sigma=1e-3, Q=1e-9, dtype=np.float64, shift=(0, 0, 0)):
+    rng = np.random.default_rng(seed)
+    x, y, z = ((rng.standard_normal(n) * sigma + s).astype(dtype) for s in shift)
+    q = np.full(n, Q / n, dtype=dtype)
+    return x, y, z, q
+
+
+def to_dev(*arrs):
+    import torch
+    return tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs)
+
+
+def set_rho(mesh, rho):
+    import torch
+    mesh.rho.copy_(torch.from_numpy(np.ascontiguousarray(rho)).cuda())
+
+
+# ------------------------------------------------------------------------------ indices
+@pytest.mark.parametrize("pdt,mdt", [(np.float64, np.float64), (np.float32, np.float32),
+                                     (np.float64, np.float32), (np.float32, np.float64)])
+def test_cell_indices_bit_exact(scb, oracle, pdt, mdt):
+    x, y, z, q = gaussian(200000, 11, dtype=pdt)
+    ref = oracle.mesh_from_particles((37, 64, 19), x, y, z, T=mdt)
+    mesh = scb.Mesh3D((37, 64, 19), *to_dev(x, y, z), T=mdt)
+    assert mesh.min_bounds == ref.min_bounds and mesh.max_bounds == ref.max_bounds and mesh.delta == ref.delta
+    got = scb.cell_indices(mesh, *to_dev(x, y, z))
+    for g, p, lo, d in zip(got, (x, y, z), ref.min_bounds, ref.delta):
+        want, _ = oracle.cell_index_and_frac(p, lo, d)
+        assert np.array_equal(g.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------ deposit
+@pytest.mark.parametrize("pdt,mdt,tol", [(np.float64, np.float64, TOL64), (np.float32, np.float32, TOL32),
+                                         (np.float64, np.float32, TOL32), (np.float32, np.float64, TOL64)])
+def test_deposit_matches_oracle(scb, oracle, record, pdt, mdt, tol):
+    x, y, z, q = gaussian(100000, 42, dtype=pdt)
+    grid = (32, 32, 32)
+    ref = oracle.mesh_from_particles(grid, x, y, z, T=np.float64 if tol == TOL32 else mdt)
+    mesh = scb.Mesh3D(grid, *to_dev(x, y, z), T=mdt)
+    if tol == TOL32:
+        # Float32 is graded against the Float64 oracle on the same (Float32-valued) geometry
+        ref.min_bounds, ref.max_bounds, ref.delta = (tuple(np.float64(v) for v in t)
+                                                     for t in (mesh.min_bounds, mesh.max_bounds, mesh.delta))
+    oracle.deposit(ref, x.astype(np.float64), y.astype(np.float64), z.astype(np.float64), q.astype(np.float64), clamp=True)
+    scb.deposit_(mesh, *to_dev(x, y, z, q))
+    got = mesh.rho.cpu().numpy()
+    check(record, "rho", got, ref.rho, tol)
+    assert abs(got.sum(dtype=np.float64) - q.sum(dtype=np.float64)) < (1e-10 if mdt == np.float64 else 1e-6) * 1e-9 * 1e3
+
+
+def test_deposit_clear_false_accumulates_and_clear_mesh(scb):
+    import torch
+    x, y, z, q = (np.array([0.5]), np.array([0.5]), np.array([0.5]), np.array([1.0]))
+    mesh = scb.Mesh3D((4, 4, 4), x, y, z)
+    d = to_dev(x, y, z, q)
+    scb.deposit_(mesh, *d)
+    s1 = float(mesh.rho.sum())
+    scb.deposit_(mesh, *d, clear=False)
+    s2 = float(mesh.rho.sum())
+    assert abs(s1 - 1.0) < 1e-10 and abs(s2 - 2 * s1) < 1e-10      # test/test_deposition.jl:63-67
+    scb.clear_mesh_(mesh)
+    assert bool(torch.all(mesh.rho == 0))                           # test/test_deposition.jl:111-112
+
+
+# -------------------------------------------------------------------------------- Green
+@pytest.mark.parametrize("icomp", [1, 2, 3])
+@pytest.mark.parametrize("offset", [(0.0, 0.0, 0.0), (0.0, 0.0, 3.1e-3)])
+def test_green_function_reference_layout(scb, oracle, record, icomp, offset):
+    """The differenced IGF is a sum of eight point-wise values that cancel to ~1/cond of their
+    size (src/green_functions.jl:103-112), so a last-ulp difference between CUDA's and the host's
+    atan/log shows up amplified by cond.  The point-wise values must agree to a few ulp; the
+    differenced block to a few ulp * cond (third-party arithmetic (2))."""
+    shape2, delta, gamma = (12, 20, 10), (1.1e-4, 0.7e-4, 2.3e-4), 3.0
+    want = oracle.get_green_function(shape2, delta, gamma, icomp, offset, np.float64)
+    point = oracle.green_pointwise(shape2, delta, gamma, icomp, offset, np.float64)
+    got = scb.get_green_function_(shape2, delta, gamma, icomp, offset).cpu().numpy()
+    inner = (slice(0, -1),) * 3
+    cond = np.abs(point).max() / np.abs(want[inner]).max()
+    eps = np.finfo(np.float64).eps
+    check(record, "igf differenced (cond %.1e)" % cond, got[inner], want[inner], max(TOL64 * 1e-2, 16 * eps * cond))
+    check(record, "igf raw last plane x", got[-1], want[-1], 16 * eps)
+    check(record, "igf raw last plane z", got[:, :, -1], want[:, :, -1], 16 * eps)
+
+
+# -------------------------------------------------------------------------------- solve
+def _solve_pair(scb, oracle, grid, lo, hi, gamma, rho, at_cathode, T=np.float64):
+    ref = oracle.mesh_from_bounds(grid, lo, hi, T=np.float64, gamma=gamma)
+    mesh = scb.Mesh3D(grid, lo, hi, T=T, gamma=gamma)
+    if T == np.float32:
+        ref.min_bounds, ref.max_bounds, ref.delta = (tuple(np.float64(v) for v in t)
+                                                     for t in (mesh.min_bounds, mesh.max_bounds, mesh.delta))
+    ref.rho[...] = rho.astype(T)
+    set_rho(mesh, rho.astype(T))
+    oracle.solve(ref, at_cathode=at_cathode)
+    scb.solve_(mesh, at_cathode=at_cathode)
+    return mesh, ref
+
+
+@pytest.mark.parametrize("grid", [(8, 8, 8), (16, 16, 16), (6, 10, 5), (2, 3, 4), (32, 32, 32), (33, 17, 40)])
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_solve_matches_oracle_f64(scb, oracle, record, grid, at_cathode):
+    rng = np.random.default_rng(sum(grid))
+    rho = rng.standard_normal(grid)
+    mesh, ref = _solve_pair(scb, oracle, grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), 3.0, rho, at_cathode)
+    got = mesh.efield.cpu().numpy()
+    for c in range(3):
+        check(record, "E%d" % c, got[..., c], ref.efield[..., c], TOL64)
+
+
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_solve_matches_oracle_f32(scb, oracle, record, at_cathode):
+    grid = (16, 24, 32)
+    rng = np.random.default_rng(5)
+    rho = rng.standard_normal(grid)
+    mesh, ref = _solve_pair(scb, oracle, grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), 2.0, rho, at_cathode, T=np.float32)
+    got = mesh.efield.cpu().numpy()
+    for c in range(3):
+        check(record, "E%d" % c, got[..., c], ref.efield[..., c], TOL32)
+
+
+def test_solve_freespace_general_offset(scb, oracle, record):
+    grid = (6, 10, 5)
+    rng = np.random.default_rng(3)
+    rho = rng.standard_normal(grid)
+    off = (0.3e-3, -0.2e-3, 1.7e-3)
+    ref = oracle.mesh_from_bounds(grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), gamma=1.5)
+    mesh = scb.Mesh3D(grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), gamma=1.5)
+    ref.rho[...] = rho
+    set_rho(mesh, rho)
+    oracle.solve_freespace(ref, off)
+    scb.solve_freespace_(mesh, off)
+    got = mesh.efield.cpu().numpy()
+    for c in range(3):
+        check(record, "E%d" % c, got[..., c], ref.efield[..., c], TOL64)
+
+
+def test_single_charge_fixtures(scb, oracle, record):
+    """test/test_solvers.jl:8-30 and the SURVEY 8c fixtures (regenerated from the oracle)."""
+    for grid, gamma in (((8, 8, 8), 1.0), ((16, 16, 16), 2.0), ((8, 8, 8), 10.0)):
+        p = (np.array([0.0]),) * 3
+        q = np.array([1.0])
+        ref, _ = oracle.full_step(grid, *p, q, gamma=gamma)
+        mesh = scb.Mesh3D(grid, *p, gamma=gamma)
+        scb.deposit_(mesh, *to_dev(*p, q))
+        scb.solve_(mesh)
+        got = mesh.efield.cpu().numpy()
+        assert abs(float(mesh.rho.sum()) - 1.0) < 1e-10
+        assert np.all(np.isfinite(got)) and np.any(got != 0)
+        for c in range(3):
+            check(record, "E%d %s g=%s" % (c, grid, gamma), got[..., c], ref.efield[..., c], TOL64)
+
+
+# --------------------------------------------------------------------------- interpolate
+@pytest.mark.parametrize("pdt,mdt,tol", [(np.float64, np.float64, 1e-13), (np.float32, np.float32, TOL32),
+                                         (np.float64, np.float32, TOL32), (np.float32, np.float64, 1e-6)])
+def test_interpolate_matches_oracle(scb, oracle, record, pdt, mdt, tol):
+    x, y, z, q = gaussian(50000, 9, dtype=pdt)
+    grid = (20, 31, 16)
+    ref = oracle.mesh_from_particles(grid, x, y, z, T=mdt)
+    mesh = scb.Mesh3D(grid, *to_dev(x, y, z), T=mdt)
+    rng = np.random.default_rng(2)
+    e = rng.standard_normal(grid + (3,)).astype(mdt)
+    ref.efield[...] = e
+    import torch
+    mesh.efield.copy_(torch.from_numpy(e).cuda())
+    want = oracle.interpolate_field(ref, x, y, z, clamp=True)
+    got = scb.interpolate_field(mesh, *to_dev(x, y, z))
+    for g, w in zip(got, want):
+        assert g.dtype == (torch.float32 if pdt == np.float32 else torch.float64)   # similar(particles_x)
+        check(record, "Einterp", g.cpu().numpy(), w, tol)
+
+
+def test_interpolate_constant_field_is_exact(scb):
+    """test/test_interpolation.jl:113-132"""
+    x = np.array([0.0, 1.0])
+    mesh = scb.Mesh3D((4, 4, 4), x, x, x)
+    mesh.efield.fill_(1.0)
+    for comp in scb.interpolate_field(mesh, *to_dev(x, x, x)):
+        assert np.allclose(comp.cpu().numpy(), 1.0, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------ pipeline
+@pytest.mark.parametrize("grid,npart,at_cathode", [((32, 32, 32), 100000, False), ((64, 64, 64), 1000000, False),
+                                                   ((16, 16, 32), 200000, True)])
+def test_full_step_matches_oracle(scb, oracle, record, grid, npart, at_cathode):
+    shift = (0, 0, 6e-3) if at_cathode else (0, 0, 0)
+    x, y, z, q = gaussian(npart, 42, shift=shift)
+    ref, want = oracle.full_step(grid, x, y, z, q, at_cathode=at_cathode)
+    d = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D(grid, *d[:3])
+    scb.deposit_(mesh, *d)
+    scb.solve_(mesh, at_cathode=at_cathode)
+    got = scb.interpolate_field(mesh, *d[:3])
+    check(record, "rho", mesh.rho.cpu().numpy(), ref.rho, TOL64)
+    e = mesh.efield.cpu().numpy()
+    for c in range(3):
+        check(record, "E%d" % c, e[..., c], ref.efield[..., c], TOL64)
+        check(record, "Einterp%d" % c, got[c].cpu().numpy(), want[c], TOL64)
+
+
+def test_fused_and_host_steps_equal_the_separate_calls(scb):
+    import torch
+    x, y, z, q = gaussian(300000, 4)
+    grid = (24, 24, 24)
+    d = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D(grid, *d[:3])
+    scb.deposit_(mesh, *d)
+    scb.solve_(mesh)
+    want = [t.clone() for t in scb.interpolate_field(mesh, *d[:3])]
+    e_want = mesh.efield.clone()
+    outs = [torch.empty_like(d[0]) for _ in range(3)]
+    scb.step_(mesh, *d, *outs)
+    for a, b in zip(outs, want):
+        assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
+    houts = [np.empty_like(x) for _ in range(3)]
+    scb.step_host_(mesh, x, y, z, q, *houts)
+    for a, b in zip(houts, want):
+        assert rel(a, b.cpu().numpy()) < 1e-12
+    assert rel(mesh.efield.cpu().numpy(), e_want.cpu().numpy()) < 1e-12
+
+
+def test_analytic_isotropic_gaussian(scb, record):
+    """test/analytical_test.jl:20-50: max|Ez - Ez_analytic| / max|Ez_analytic| < 0.10 at 32^3."""
+    from scipy.special import erf
+    x, y, z, q = gaussian(1000000, 123)
+    for grid in ((32, 32, 32), (64, 64, 64)):
+        d = to_dev(x, y, z, q)
+        mesh = scb.Mesh3D(grid, *d[:3], total_charge=1e-9)
+        scb.deposit_(mesh, *d)
+        scb.solve_(mesh)
+        zc = np.array([mesh.min_bounds[2] + k * mesh.delta[2] for k in range(grid[2])])
+        xi = int(np.argmin(np.abs([mesh.min_bounds[0] + i * mesh.delta[0] for i in range(grid[0])])))
+        yi = int(np.argmin(np.abs([mesh.min_bounds[1] + i * mesh.delta[1] for i in range(grid[1])])))
+        ez = mesh.efield[xi, yi, :, 2].cpu().numpy()
+        r, s, Q, eps0 = np.abs(zc), 1e-3, 1e-9, 8.8541878128e-12
+        an = Q / (4 * np.pi * eps0 * r ** 3) * (erf(r / (np.sqrt(2) * s)) - np.sqrt(2 / np.pi) * r / s * np.exp(-(r / s) ** 2 / 2)) * zc
+        err = np.abs(ez - an).max() / np.abs(an).max()
+        record("analytic Ez %s" % (grid,), err, 0.10)
+        assert err < 0.10
+
+
+def test_errors_follow_the_reference(scb):
+    """test/test_mesh.jl:78-93"""
+    E = scb.ErrorException
+    for bad in ((0, 2, 2), (2, 1, 2), (2, 2, 1)):
+        with pytest.raises(E):
+            scb.Mesh3D(bad, [0.0], [0.0], [0.0])
+    with pytest.raises(E):
+        scb.Mesh3D((2, 2, 2), [], [], [])
+    with pytest.raises(E):
+        scb.Mesh3D((4, 4, 4), [0.0, 1.0], [0.0], [0.0])
+    with pytest.raises(E):
+        scb.Mesh3D((2, 2, 2), (0, 0, 0), (0, 0, 0))
+    mesh = scb.Mesh3D((4, 4, 4), [0.5], [0.5], [0.5])
+    with pytest.raises(E):
+        scb.deposit_(mesh, [0.5, 0.6], [0.5], [0.5], [1.0])
