@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- full deposit -> IGF/FFT solve -> interpolate step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload large|pipeline|cathode|analytic|basic] [--dtype f64|f32]
+
+One JSON line on stdout (rank 0).  `value` = particles/s with the particle arrays resident in HBM,
+`e2e` = the same metric through scb_step_host with HOST (pinned) particle buffers, copies inside the
+timed region.  `roofline` describes the dominant kernel of the step; `stage_roofline` every stage.
+`cpu_baseline` / `--impl reference` time oracle/cpu_reference.py (C restatement of the reference's
+structure + threaded pocketfft; Julia is not installed) on the host cores of the same box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (particles, grid, at_cathode, z shift in sigma)   -- BASELINE.json configs
+    "basic": (100_000, (32, 32, 32), False, 0.0),
+    "analytic": (1_000_000, (64, 64, 64), False, 0.0),
+    "pipeline": (10_000_000, (128, 128, 128), False, 0.0),
+    "cathode": (10_000_000, (128, 128, 256), True, 6.0),
+    "large": (100_000_000, (256, 256, 256), False, 0.0),
+}
+SIGMA, QTOT = 1.0e-3, 1.0e-9
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(npart, grid, s, at_cathode):
+    """SURVEY.md 8(d) / DESIGN.md: algorithmic bytes per launch of every stage."""
+    nx, ny, nz = grid
+    L = [8] * 3
+    for a, n in enumerate(grid):
+        while L[a] < 2 * n:
+            L[a] *= 2
+    ng = nx * ny * nz
+    kx = L[0] // 2 + 1
+    A = kx * ny * nz * 2 * s
+    B = kx * L[1] * nz * 2 * s
+    G = 3 * kx * (L[1] // 2 + 1) * (L[2] // 2 + 1) * s
+    Gimg = 3 * kx * L[1] * L[2] * 2 * s if at_cathode else 0
+    return {
+        "deposit": 4 * npart * s + ng * s,
+        "interpolate": 6 * npart * s + 3 * ng * s,
+        "F1": ng * s + A, "F2": A + B, "Z": B + G + Gimg + 3 * B, "B2": 3 * (A + B), "B3": 3 * (A + ng * s),
+    }
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in self.rows), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=150.0):
+    """The reference's CPU structure on the host cores.  One step = the full-grid solve plus
+    deposit/interpolate on a bounded particle sample, particle time scaled to the full count."""
+    from oracle import spacecharge_oracle as so
+    from oracle.cpu_reference import RefPort
+
+    cores = os.cpu_count() or 1
+    nsample = min(npart, 4_000_000)
+    rng = np.random.default_rng(42)
+    x, y, z = (rng.standard_normal(nsample) * SIGMA for _ in range(3))
+    z = z + zshift * SIGMA
+    q = np.full(nsample, QTOT / npart)
+    mesh = so.mesh_from_particles(grid, x, y, z)
+    rp = RefPort(grid, mesh.min_bounds, mesh.delta, 1.0, threads=cores)
+    scale = npart / nsample
+    times, parts = [], []
+    t_begin = time.perf_counter()
+    done = 0
+    for it in range(warmup + steps):
+        _, t = rp.timed_step(x, y, z, q, at_cathode, mesh.max_bounds)
+        if it >= min(warmup, 1) or steps == 0:
+            times.append(t["solve_s"] + scale * (t["deposit_s"] + t["interpolate_s"]))
+            parts.append(t)
+            done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            break
+    t_step = float(np.mean(times))
+    last = parts[-1]
+    return {
+        "value": npart / t_step, "unit": "particles/s", "cores": cores, "kind": "port",
+        "sample": ("full %dx%dx%d solve + deposit/interpolate of %d of %d particles, particle time scaled x%.0f; "
+                   "C restatement of the reference structure + scipy/pocketfft C2C (FFTW absent); %d step(s) timed"
+                   % (grid + (nsample, npart, scale, done))),
+        "ms_per_step": 1e3 * t_step,
+        "stages_ms": {"deposit": 1e3 * scale * last["deposit_s"], "solve": 1e3 * last["solve_s"],
+                      "interpolate": 1e3 * scale * last["interpolate_s"]},
+        "steps_timed": done,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--particles", type=int, default=0, help="override the particle count (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    npart, grid, at_cathode, zshift = WORKLOADS[args.workload]
+    if args.particles:
+        npart = args.particles
+    s = 8 if args.dtype == "f64" else 4
+    config = {"workload": "%s: Gaussian bunch %.0e particles, %dx%dx%d grid%s" % (
+        args.workload, npart, grid[0], grid[1], grid[2], ", cathode image" if at_cathode else ""),
+        "particles": npart, "grid": list(grid), "at_cathode": at_cathode, "sigma_m": SIGMA,
+        "l2": "inputs larger than L2 (particle arrays %.1f GB per step)" % (4 * npart * s / 1e9),
+        "parallelism": "particles sharded over %d GPU(s), rho all-reduced, solve replicated" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_run(npart, grid, at_cathode, zshift, args.steps, args.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": "particles/sec for full deposit+solve+interp step", "value": cb["value"],
+            "unit": "particles/s", "n_gpus": args.gpus, "steps": cb["steps_timed"], "steps_requested": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "stages_ms": cb["stages_ms"],
+            "e2e": {"value": cb["value"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    scb = load_package()
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+        group = dist.group.WORLD
+
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    npdt = np.float64 if args.dtype == "f64" else np.float32
+    n_local = npart // world + (1 if rank < npart % world else 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(42 + rank)
+    x, y, z = (torch.randn(n_local, generator=gen, device=dev, dtype=tdt) * SIGMA for _ in range(3))
+    if zshift:
+        z += zshift * SIGMA
+    q = torch.full((n_local,), QTOT / npart, device=dev, dtype=tdt)
+    ex, ey, ez = (torch.empty_like(x) for _ in range(3))
+
+    mesh = scb.Mesh3D(grid, x, y, z, T=npdt, total_charge=QTOT, group=group)   # built once, outside the timed region
+    hd = mesh.handle
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = hd.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    launches = (hd.launch_count() - launches0) + (args.steps if world > 1 else 0)  # + NCCL all-reduce
+    sampler.stop_flag = True
+
+    # per-stage device times (library CUDA events), min over a few extra steps
+    hd.enable_timing(True)
+    stage = None
+    for _ in range(5):
+        scb.deposit_(mesh, x, y, z, q)
+        scb.solve_(mesh, at_cathode=at_cathode)
+        hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 1 if s == 8 else 0,
+                                        mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                        ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+        t = hd.timing()
+        cur = {"deposit": t["deposit_ms"], "solve": t["solve_ms"], "interpolate": t["interpolate_ms"]}
+        cur.update(dict(zip(("F1", "F2", "Z", "B2", "B3"), t["pass_ms"])))
+        stage = cur if stage is None else {k: min(stage[k], cur[k]) for k in cur}
+    # cold geometry: Green spectrum rebuilt (the reference rebuilds it on every solve)
+    hd.drop_green_cache()
+    scb.solve_(mesh, at_cathode=at_cathode)
+    tc = hd.timing()
+    cold = {"solve_cold_ms": tc["solve_ms"], "green_build_ms": tc["green_ms"]}
+    hd.enable_timing(False)
+
+    peak, peak_src = measured_peak()
+    ab = algorithmic_bytes(n_local, grid, s, at_cathode)
+    stage_roof = {}
+    for k in ("deposit", "interpolate", "F1", "F2", "Z", "B2", "B3"):
+        gbs = ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0
+        stage_roof[k] = {"ms": round(stage[k], 4), "alg_MB": round(ab[k] / 1e6, 1), "GBps": round(gbs, 1),
+                         "frac": round(gbs / peak, 4)}
+    kernel_names = {"deposit": "k_deposit", "interpolate": "k_interpolate", "F1": "k_x_r2c", "F2": "k_lines<-1>",
+                    "Z": "k_z_fused", "B2": "k_lines<+1>", "B3": "k_x_c2r"}
+    dom = max(stage_roof, key=lambda k: stage_roof[k]["ms"])
+    roofline = {"kernel": kernel_names[dom], "stage": dom, "bound": "hbm", "achieved": stage_roof[dom]["GBps"],
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": None}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tr):
+        with open(tr) as f:
+            roofline["traffic"] = json.load(f).get(args.workload + "_" + args.dtype, {}).get(kernel_names[dom])
+
+    # end to end: host (pinned) particle buffers through scb_step_host, copies inside the timed region
+    e2e = None
+    if not args.no_e2e and world == 1:
+        hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
+        hex_, hey, hez = (torch.empty_like(hx).pin_memory() for _ in range(3))
+        for _ in range(2):
+            scb.step_host_(mesh, hx, hy, hz, hq, hex_, hey, hez, at_cathode=at_cathode)
+        ksteps = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            scb.step_host_(mesh, hx, hy, hz, hq, hex_, hey, hez, at_cathode=at_cathode)   # synchronous on return
+        t_e2e = (time.perf_counter() - t0) / ksteps
+        e2e = {"value": npart / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": 4 * n_local * s,
+               "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * t_e2e, "steps": ksteps,
+               "api": "scb_step_host (pinned host particle arrays in, pinned host E arrays out)"}
+    elif not args.no_e2e:
+        # sharded: every rank feeds its own shard from pinned host memory
+        hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
+        hex_, hey, hez = (torch.empty_like(hx).pin_memory() for _ in range(3))
+
+        def host_step():
+            x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
+            z.copy_(hz, non_blocking=True); q.copy_(hq, non_blocking=True)
+            scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
+            hex_.copy_(ex, non_blocking=True); hey.copy_(ey, non_blocking=True); hez.copy_(ez, non_blocking=True)
+            torch.cuda.synchronize()
+        host_step()
+        ksteps = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            host_step()
+        barrier()
+        tt = torch.tensor([(time.perf_counter() - t0) / ksteps], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": npart / float(tt.item()), "unit": "particles/s", "h2d_bytes_per_step": 4 * n_local * s,
+               "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * float(tt.item()), "steps": ksteps,
+               "api": "pinned host shards -> step_ -> pinned host outputs, per rank"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del x, y, z, q, ex, ey, ez
+        cb = cpu_reference_run(npart, grid, at_cathode, zshift, 1, 0, budget_s=60.0)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline["stages_ms"] = cb["stages_ms"]
+
+    if rank == 0:
+        line = {
+            "metric": "particles/sec for full deposit+solve+interp step", "value": npart / (ms_per_step * 1e-3),
+            "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.summary(), "roofline": roofline, "stage_roofline": stage_roof,
+            "solve_ms": stage["solve"], "cold_geometry": cold, "cpu_baseline": cpu_baseline,
+            "workspace_GB": hd.workspace_bytes() / 1e9,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -196,7 +196,7 @@ class Mesh3D:
             if not (len(px) == len(py) == len(pz)):
                 raise ErrorException("Particle coordinate arrays must have the same length.")
             dev_hint = px.device.index if isinstance(px, torch.Tensor) and px.device.type == "cuda" else None
-            lo, hi, delta = self._auto_bounds(grid_size, px, py, pz, Tn, dev_hint if device is None else device, handle)
+            lo, hi, delta = self._auto_bounds(grid_size, px, py, pz, Tn, dev_hint if device is None else device, handle, group)
         else:
             raise ErrorException("Mesh3D(grid_size, x, y, z) or Mesh3D(grid_size, min_bounds, max_bounds)")
         if device is None:
@@ -219,7 +219,7 @@ class Mesh3D:
         self._workspace = None
 
     @staticmethod
-    def _auto_bounds(grid_size, px, py, pz, Tn, device, handle):
+    def _auto_bounds(grid_size, px, py, pz, Tn, device, handle, group=None):
         """src/mesh.jl:118-156: extrema and first delta in the particles' precision, the 1e-6
         padding and the final delta in Float64, zero delta -> 1e-6, then the cast to T."""
         torch = _torch()
@@ -239,6 +239,15 @@ class Mesh3D:
                 if isinstance(p, torch.Tensor):
                     p = p.detach().cpu().numpy()
                 ext.append(_extrema_host(p))
+        if group is not None:
+            # particle-sharded run: the bunch extrema are the extrema over all ranks
+            import torch.distributed as dist
+            dev = "cuda:%d" % device if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"
+            tlo = torch.tensor([float(e[0]) for e in ext], dtype=torch.float64, device=dev)
+            thi = torch.tensor([float(e[1]) for e in ext], dtype=torch.float64, device=dev)
+            dist.all_reduce(tlo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(thi, op=dist.ReduceOp.MAX, group=group)
+            ext = [(e[2](tlo[a].item()), e[2](thi[a].item()), e[2]) for a, e in enumerate(ext)]
         lo1, hi1, d1 = [], [], []
         for (lo, hi, P), n in zip(ext, grid_size):
             d0 = P((hi - lo) / P(n - 1))
