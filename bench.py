@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="override the particle count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stages-only", action="store_true", help="print only the per-stage device times (tuning)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +213,18 @@ def main():
     for _ in range(max(args.warmup, 3)):
         scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
     barrier()
+    if args.stages_only:
+        hd.enable_timing(True)
+        stage = None
+        for _ in range(5):
+            scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
+            t = hd.timing()
+            cur = {"deposit": t["deposit_ms"], "solve": t["solve_ms"], "interpolate": t["interpolate_ms"]}
+            cur.update(dict(zip(("F1", "F2", "Z", "B2", "B3"), t["pass_ms"])))
+            stage = cur if stage is None else {k: min(stage[k], cur[k]) for k in cur}
+        print(json.dumps({"lib": os.environ.get("SCB_LIB", "default"), "dtype": args.dtype, "workload": args.workload,
+                          "stages_ms": {k: round(v, 4) for k, v in stage.items()}}))
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -242,12 +242,10 @@ class Mesh3D:
         if group is not None:
             # particle-sharded run: the bunch extrema are the extrema over all ranks
             import torch.distributed as dist
+            from .sharding import global_extrema
             dev = "cuda:%d" % device if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"
-            tlo = torch.tensor([float(e[0]) for e in ext], dtype=torch.float64, device=dev)
-            thi = torch.tensor([float(e[1]) for e in ext], dtype=torch.float64, device=dev)
-            dist.all_reduce(tlo, op=dist.ReduceOp.MIN, group=group)
-            dist.all_reduce(thi, op=dist.ReduceOp.MAX, group=group)
-            ext = [(e[2](tlo[a].item()), e[2](thi[a].item()), e[2]) for a, e in enumerate(ext)]
+            glo, ghi = global_extrema([e[0] for e in ext], [e[1] for e in ext], group, dev)
+            ext = [(e[2](glo[a]), e[2](ghi[a]), e[2]) for a, e in enumerate(ext)]
         lo1, hi1, d1 = [], [], []
         for (lo, hi, P), n in zip(ext, grid_size):
             d0 = P((hi - lo) / P(n - 1))
@@ -314,8 +312,8 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
     hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
                                 mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
     if mesh.group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(mesh._rho, group=mesh.group)
+        from .sharding import allreduce_rho
+        allreduce_rho(mesh._rho, mesh.group)
 
 
 def solve_(mesh: Mesh3D, at_cathode: bool = False) -> None:

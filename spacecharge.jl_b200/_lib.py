@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspacecharge_b200.so")
+# SCB_LIB selects an experimental build variant (spacecharge.jl_b200/build.py --tag); default: the product library
+LIB_PATH = os.environ.get("SCB_LIB") or os.path.join(HERE, "lib", "libspacecharge_b200.so")
 
 SCB_F32, SCB_F64 = 0, 1
 SCB_OK = 0

@@ -40,17 +40,22 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, tag: str = "", defines=()) -> str:
+    """tag/defines build an experimental variant next to the product library
+    (lib/libspacecharge_b200_<tag>.so), selected at run time with SCB_LIB=<path>."""
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = OBJDIR + ("_" + tag if tag else "")
+    lib_path = LIB if not tag else os.path.join(LIBDIR, "libspacecharge_b200_%s.so" % tag)
+    os.makedirs(objdir, exist_ok=True)
     hdrs = _headers()
+    defs = ["-D" + d for d in defines]
 
     def compile_one(item):
         name, extra = item
         src = os.path.join(CSRC, name)
-        obj = os.path.join(OBJDIR, name.replace(".cu", ".o"))
+        obj = os.path.join(objdir, name.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + COMMON + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (name, r.stdout, r.stderr))
@@ -60,13 +65,20 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(UNITS))) as ex:
         objs = list(ex.map(compile_one, UNITS.items()))
-    if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if force or _stale(lib_path, objs):
+        cmd = [NVCC, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--tag", default="")
+    ap.add_argument("-D", action="append", default=[])
+    a = ap.parse_args()
+    print(build_library(force=a.force, verbose=a.v, tag=a.tag, defines=a.D))

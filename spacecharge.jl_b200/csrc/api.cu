@@ -56,6 +56,8 @@ struct scb_handle {
     std::vector<GreenEntry> green;
     unsigned long long stamp = 0;
     unsigned long long* d_bounds = nullptr;
+    void* packed = nullptr;       // node-major copy of efield for the gather (32 bytes per node)
+    size_t packed_bytes = 0;
     int64_t launches = 0;
     // timing
     bool timing = false;
@@ -148,6 +150,43 @@ int get_twiddles(scb_handle* h, int N, const cx_t<T>** out) {
     SCB_CUDA(h, cudaMemcpy(d, host.data(), sizeof(cx_t<T>) * N, cudaMemcpyHostToDevice));
     h->twiddles[{N, is64}] = d;
     *out = static_cast<const cx_t<T>*>(d);
+    return SCB_OK;
+}
+
+int ensure_packed(scb_handle* h, size_t bytes) {
+    if (bytes <= h->packed_bytes) return SCB_OK;
+    if (h->packed) {
+        SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+        SCB_CUDA(h, cudaFree(h->packed));
+        h->packed = nullptr;
+        h->packed_bytes = 0;
+    }
+    if (cudaMalloc(&h->packed, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, SCB_ERR_ALLOC, "packed-field allocation failed");
+    }
+    h->packed_bytes = bytes;
+    return SCB_OK;
+}
+
+// gather: repack the field node-major when there are enough particles to pay for the extra pass
+int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, const void* efield,
+                    int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready) {
+    const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
+    const bool use_packed = (packed_ready && *packed_ready) || np * 4 >= ng;
+    if (!use_packed) {
+        SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream));
+        h->launches += 1;
+        return SCB_OK;
+    }
+    if (!(packed_ready && *packed_ready)) {
+        SCB_TRY(ensure_packed(h, (size_t)ng * 32));
+        SCB_CUDA(h, launch_pack_efield(mdt, efield, h->packed, g, h->stream));
+        h->launches += 1;
+        if (packed_ready) *packed_ready = true;
+    }
+    SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream));
+    h->launches += 1;
     return SCB_OK;
 }
 
@@ -548,6 +587,7 @@ int scb_destroy(scb_handle* h) {
     for (auto& kv : h->twiddles) cudaFree(kv.second);
     if (h->arena) cudaFree(h->arena);
     if (h->stage) cudaFree(h->stage);
+    if (h->packed) cudaFree(h->packed);
     if (h->d_bounds) cudaFree(h->d_bounds);
     if (h->ev_ready)
         for (auto& e : h->ev) cudaEventDestroy(e);
@@ -660,10 +700,9 @@ int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
     SCB_TRY(check_grid(h, n));
     SCB_CUDA(h, cudaSetDevice(h->device));
     tick(h, 4);
-    SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, make_geom(n, min_bounds, delta), ex, ey, ez, h->stream));
+    if (np > 0) SCB_TRY(run_interpolate(h, np, x, y, z, pdt, efield, mdt, make_geom(n, min_bounds, delta), ex, ey, ez, nullptr));
     tick(h, 5);
     h->t_interp = true;
-    if (np > 0) h->launches += 1;
     return SCB_OK;
 }
 
@@ -785,10 +824,22 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
         h->launches += 1;
     }
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    bool packed_ready = false;
+    if (np * 4 >= (int64_t)n[0] * n[1] * n[2]) {
+        SCB_TRY(ensure_packed(h, (size_t)n[0] * n[1] * n[2] * 32));
+        SCB_CUDA(h, launch_pack_efield(mdt, efield, h->packed, g, h->stream));
+        h->launches += 1;
+        packed_ready = true;
+    }
     for (int c = 0; c < nchunk; ++c) {
         const int64_t o = (int64_t)c * chunk, m = (np - o) < chunk ? (np - o) : chunk;
-        SCB_CUDA(h, launch_interpolate(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, efield, g, d[4] + o * es,
-                                       d[5] + o * es, d[6] + o * es, h->stream));
+        if (packed_ready) {
+            SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, h->packed, g,
+                                                  d[4] + o * es, d[5] + o * es, d[6] + o * es, h->stream));
+        } else {
+            SCB_CUDA(h, launch_interpolate(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, efield, g, d[4] + o * es,
+                                           d[5] + o * es, d[6] + o * es, h->stream));
+        }
         h->launches += 1;
         SCB_CUDA(h, cudaEventRecord(h->chunk_ev[nchunk + c], h->stream));
         SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[nchunk + c], 0));
@@ -809,7 +860,7 @@ int scb_drop_green_cache(scb_handle* h) {
 
 int64_t scb_workspace_bytes(const scb_handle* h) {
     if (!h) return 0;
-    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes;
+    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes;
     for (auto& e : h->green) b += (int64_t)e.bytes;
     return b;
 }

@@ -25,6 +25,17 @@ namespace scb {
 __host__ __device__ constexpr int tx_for(int N) {
     return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? 8 : N == 128 ? 16 : 32;
 }
+// lockstep lines of the fused z pass (its register footprint is twice that of a plain pass, so
+// it runs narrower CTAs to keep two of them resident per SM)
+#ifndef SCB_ZTX_BIG
+#define SCB_ZTX_BIG 8
+#endif
+#ifndef SCB_Z_MINBLOCKS
+#define SCB_Z_MINBLOCKS 1
+#endif
+__host__ __device__ constexpr int tz_for(int N) {
+    return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? SCB_ZTX_BIG : N == 128 ? 16 : 32;
+}
 // line pairs per CTA in the x passes
 __host__ __device__ constexpr int lp_for(int N) { return (N / 8) >= 256 ? 1 : 256 / (N / 8); }
 
@@ -90,19 +101,54 @@ struct ZParams {
     long long H_scomp;
 };
 
+// cp.async of one real (4 or 8 bytes) from global to shared memory: lets the Green-spectrum
+// values of the next field component travel while the inverse FFT of the current one runs,
+// without holding them in registers (the kernel already sits at the 128-register limit).
+template <typename T> __device__ __forceinline__ void cp_async_real(T* smem_dst, const T* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(sizeof(T)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename T, int N, int KIND>
-__global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_z_fused(const ZParams<T> p) {
+__global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fused(const ZParams<T> p) {
     using C = cx_t<T>;
-    constexpr int TX = tx_for(N);
+    constexpr int TX = tz_for(N);
     constexpr int TPL = N / 8;
+    constexpr bool USE_S = (KIND == GREEN_FREE || KIND == GREEN_CATHODE);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tx = threadIdx.x, j = threadIdx.y;
     const int kx = blockIdx.x * TX + tx;
     const int ky = blockIdx.y;
     const bool valid = kx < p.ninner;
     LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
+    // second buffer (cathode only) keeps the forward spectrum so that bin (-kz) can be read
+    LayoutRows<C, TX> laym(reinterpret_cast<C*>(smem_raw + LayoutRows<C, TX>::bytes(N)), tx);
+    // staging area for the compressed spectrum: slot (q, j, tx) is private to this thread
+    T* sstage = reinterpret_cast<T*>(smem_raw + (KIND == GREEN_CATHODE ? 2 : 1) * LayoutRows<C, TX>::bytes(N)) +
+                (j * TX + tx);
+    constexpr int SSTRIDE = TPL * TX;
     const long long plane = (long long)p.PX * p.Ly;
+    const int Lyh = p.Ly / 2;
+    const int kyf = ky <= Lyh ? ky : p.Ly - ky;  // folded ky
 
+    auto prefetch_S = [&](int c) {
+        if constexpr (USE_S) {
+            if (valid) {
+                const T* base = p.S + c * p.S_scomp + kx + (long long)p.PX * kyf;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int kz = j + q * TPL;
+                    const int kzf = kz <= N / 2 ? kz : N - kz;
+                    cp_async_real<T>(sstage + q * SSTRIDE, base + (long long)p.PX * (Lyh + 1) * kzf);
+                }
+            }
+            cp_async_commit();
+        }
+    };
+
+    prefetch_S(0);
     C spec[8];
     {
         const C* src = p.in + (long long)ky * p.PX + kx;
@@ -114,28 +160,23 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_z_fused(const ZParams<T
     }
     fft_line<T, N, -1>(spec, lay, j, p.tw);
 
-    // second buffer keeps the forward spectrum so that bin (-kz) can be read by other threads
-    LayoutRows<C, TX> laym(reinterpret_cast<C*>(smem_raw + LayoutRows<C, TX>::bytes(N)), tx);
     if constexpr (KIND == GREEN_CATHODE) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) laym.st(j + q * TPL, spec[q]);
         __syncthreads();
     }
 
-    const int Lyh = p.Ly / 2;
-    const int kyf = ky <= Lyh ? ky : p.Ly - ky;  // folded ky
-
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
         C w[8];
+        if constexpr (USE_S) cp_async_wait_all();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int kz = j + q * TPL;
             C acc = cmake<C>(0, 0);
             if (valid) {
-                if constexpr (KIND == GREEN_FREE || KIND == GREEN_CATHODE) {
-                    const int kzf = kz <= N / 2 ? kz : N - kz;
-                    T s = __ldg(p.S + c * p.S_scomp + kx + (long long)p.PX * (kyf + (long long)(Lyh + 1) * kzf));
+                if constexpr (USE_S) {
+                    T s = sstage[q * SSTRIDE];
                     if ((c == 1 && ky > Lyh) || (c == 2 && kz > N / 2)) s = -s;
                     // (a + ib) * (i s) = s * (-b + i a)
                     acc = cmake<C>(-spec[q].y * s, spec[q].x * s);
@@ -152,6 +193,7 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_z_fused(const ZParams<T
             }
             w[q] = acc;
         }
+        if (c < 2) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
         fft_line<T, N, +1>(w, lay, j, p.tw);
         C* dst = p.out + c * p.out_scomp + (long long)ky * p.PX + kx;
 #pragma unroll

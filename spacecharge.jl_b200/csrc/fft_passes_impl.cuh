@@ -37,15 +37,16 @@ template <> cudaError_t launch_z_fused<SCB_T>(int N, int kind, const ZParams<SCB
     cudaError_t e = cudaErrorInvalidValue;
 #define X(NN)                                                                                     \
     if (N == NN) {                                                                                \
-        constexpr int TX = tx_for(NN);                                                            \
+        constexpr int TX = tz_for(NN);                                                            \
         const size_t sm1 = LayoutRows<C, TX>::bytes(NN);                                          \
         dim3 grid((p.ninner + TX - 1) / TX, p.Ly), block(TX, NN / 8);                             \
+        const size_t sst = (size_t)TX * NN * sizeof(SCB_T);                                       \
         if (kind == GREEN_FREE) {                                                                 \
-            e = set_smem(k_z_fused<SCB_T, NN, GREEN_FREE>, sm1);                                  \
-            if (e == cudaSuccess) k_z_fused<SCB_T, NN, GREEN_FREE><<<grid, block, sm1, s>>>(p);   \
+            e = set_smem(k_z_fused<SCB_T, NN, GREEN_FREE>, sm1 + sst);                            \
+            if (e == cudaSuccess) k_z_fused<SCB_T, NN, GREEN_FREE><<<grid, block, sm1 + sst, s>>>(p); \
         } else if (kind == GREEN_CATHODE) {                                                       \
-            e = set_smem(k_z_fused<SCB_T, NN, GREEN_CATHODE>, 2 * sm1);                           \
-            if (e == cudaSuccess) k_z_fused<SCB_T, NN, GREEN_CATHODE><<<grid, block, 2 * sm1, s>>>(p); \
+            e = set_smem(k_z_fused<SCB_T, NN, GREEN_CATHODE>, 2 * sm1 + sst);                     \
+            if (e == cudaSuccess) k_z_fused<SCB_T, NN, GREEN_CATHODE><<<grid, block, 2 * sm1 + sst, s>>>(p); \
         } else {                                                                                  \
             e = set_smem(k_z_fused<SCB_T, NN, GREEN_FULL>, sm1);                                  \
             if (e == cudaSuccess) k_z_fused<SCB_T, NN, GREEN_FULL><<<grid, block, sm1, s>>>(p);   \

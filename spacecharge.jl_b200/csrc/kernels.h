@@ -35,6 +35,10 @@ cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const 
                            const void* q, void* rho, const Geom3& g, cudaStream_t s);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
+// node-major repack of efield (32 bytes per node) and the gather that reads it
+cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s);
+cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                                      const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
 cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                               const Geom3& g, long long* ix, long long* iy, long long* iz, cudaStream_t s);
 // partial[0..2] = min, partial[3..5] = max as doubles; must be initialised by the launcher
