@@ -210,6 +210,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.stages_only:
+        sampler.start()   # samples through warm-up and the timed region (the region itself lasts ~0.1 s)
     for _ in range(max(args.warmup, 3)):
         scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
     barrier()
@@ -225,9 +228,6 @@ def main():
         print(json.dumps({"lib": os.environ.get("SCB_LIB", "default"), "dtype": args.dtype, "workload": args.workload,
                           "stages_ms": {k: round(v, 4) for k, v in stage.items()}}))
         return
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = hd.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

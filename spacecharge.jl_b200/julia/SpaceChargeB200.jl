@@ -1,0 +1,228 @@
+"""
+    SpaceChargeB200
+
+Drop-in replacement for the hot path of SpaceCharge.jl v1.2.0 on NVIDIA B200 (sm_100a).
+
+Same exported surface as the reference (`src/SpaceCharge.jl:17`): `Mesh3D, deposit!, clear_mesh!,
+interpolate_field, solve!`, same positional/keyword arguments, same `ErrorException`s.  Every
+computation is a `ccall` into `libspacecharge_b200.so` (C ABI: `include/spacecharge_b200.h`);
+there is no CPU backend and no KernelAbstractions dispatch.  Arrays are `CuArray`s owned by Julia.
+
+NOTE: Julia is not installed in the build image, so this shim has never been executed there; it is
+kept mechanical (argument marshalling only).  The tested twin of this file is the Python/ctypes
+mirror `spacecharge.jl_b200/__init__.py`, which binds exactly the same symbols.
+"""
+module SpaceChargeB200
+
+using CUDA
+
+export Mesh3D, deposit!, clear_mesh!, interpolate_field, solve!
+
+const CLIGHT = 299792458.0               # src/utils.jl:7
+const FPEI = CLIGHT^2 * 1.0e-7           # src/utils.jl:8
+
+const LIB = get(ENV, "SPACECHARGE_B200_LIB", "libspacecharge_b200.so")
+
+const SCB_F32 = Cint(0)
+const SCB_F64 = Cint(1)
+dtag(::Type{Float32}) = SCB_F32
+dtag(::Type{Float64}) = SCB_F64
+
+# ---- handle (one per task/stream, like the C ABI requires) --------------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+end
+
+function Handle(; device::Integer = CUDA.deviceid(CUDA.device()), stream = CUDA.stream())
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:scb_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+               device, Base.unsafe_convert(Ptr{Cvoid}, stream.handle), C_NULL, out)
+    rc == 0 || error("scb_create failed with code $rc (an sm_100 GPU is required; there is no CPU fallback)")
+    h = Handle(out[])
+    finalizer(x -> ccall((:scb_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
+
+const _handle = Ref{Union{Nothing, Handle}}(nothing)
+default_handle() = (_handle[] === nothing && (_handle[] = Handle()); _handle[]::Handle)
+
+function check(h::Handle, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:scb_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr))
+    error(msg)   # ErrorException, like the reference's error("...")
+end
+
+# ---- Mesh3D: same fields as src/mesh.jl:19-34 ---------------------------------------------------
+mutable struct Mesh3D{T <: AbstractFloat, A <: AbstractArray{T}, B <: AbstractArray{T}}
+    grid_size::NTuple{3, Int}
+    min_bounds::NTuple{3, T}
+    max_bounds::NTuple{3, T}
+    delta::NTuple{3, T}
+    gamma::T
+    total_charge::T
+    rho::A
+    efield::B
+    _workspace::Union{Nothing, Handle}   # the reference keeps FFT plans here; we keep the scb handle
+end
+
+_n(m::Mesh3D) = Int64[m.grid_size...]
+_f3(t) = Float64[t...]
+handle(m::Mesh3D) = (m._workspace === nothing && (m._workspace = default_handle()); m._workspace::Handle)
+
+"""
+    Mesh3D(grid_size, particles_x, particles_y, particles_z; T=Float64, gamma=1.0, total_charge=0.0)
+
+Bounds from the particle extrema, arithmetic of src/mesh.jl:118-156 (extrema and first delta in the
+particles' precision, 1e-6 padding and final delta in Float64, zero delta -> 1e-6, then cast to T).
+For `CuArray` particles the extrema come from `scb_bounds` (one fused device reduction).
+"""
+function Mesh3D(grid_size::NTuple{3, Int}, particles_x, particles_y, particles_z;
+                T::Type{<:AbstractFloat} = Float64, backend = nothing, gamma::Real = 1.0, total_charge::Real = 0.0)
+    any(grid_size .<= 1) && error("All elements of grid_size must be at least 2.")
+    (isempty(particles_x) || isempty(particles_y) || isempty(particles_z)) && error("Particle arrays cannot be empty.")
+    (length(particles_x) == length(particles_y) == length(particles_z)) ||
+        error("Particle coordinate arrays must have the same length.")
+    if particles_x isa CuArray
+        P = eltype(particles_x)
+        lo = zeros(Float64, 3); hi = zeros(Float64, 3)
+        h = default_handle()
+        check(h, ccall((:scb_bounds, LIB), Cint,
+                       (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}),
+                       h.ptr, length(particles_x), particles_x, particles_y, particles_z, dtag(P), lo, hi))
+        mins = (P(lo[1]), P(lo[2]), P(lo[3])); maxs = (P(hi[1]), P(hi[2]), P(hi[3]))
+    else
+        ex = (extrema(particles_x), extrema(particles_y), extrema(particles_z))
+        mins = (ex[1][1], ex[2][1], ex[3][1]); maxs = (ex[1][2], ex[2][2], ex[3][2])
+    end
+    delta = ntuple(i -> (maxs[i] - mins[i]) / (grid_size[i] - 1), 3)
+    mins = ntuple(i -> mins[i] - 1e-6 * delta[i], 3)
+    maxs = ntuple(i -> maxs[i] + 1e-6 * delta[i], 3)
+    delta = ntuple(i -> (maxs[i] - mins[i]) / (grid_size[i] - 1), 3)
+    delta = ntuple(i -> delta[i] == 0 ? 1e-6 : delta[i], 3)
+    rho = CUDA.zeros(T, grid_size...)
+    efield = CUDA.zeros(T, grid_size..., 3)
+    return Mesh3D{T, typeof(rho), typeof(efield)}(grid_size, T.(mins), T.(maxs), T.(delta), T(gamma), T(total_charge),
+                                                  rho, efield, nothing)
+end
+
+"""
+    Mesh3D(grid_size, min_bounds, max_bounds; T=Float64, gamma=1.0, total_charge=0.0)
+
+Manual bounds (src/mesh.jl:196-238): bounds cast to T first, delta computed in T.
+"""
+function Mesh3D(grid_size::NTuple{3, Int}, min_bounds::NTuple{3, Real}, max_bounds::NTuple{3, Real};
+                T::Type{<:AbstractFloat} = Float64, backend = nothing, gamma::Real = 1.0, total_charge::Real = 0.0)
+    any(grid_size .<= 1) && error("All elements of grid_size must be at least 2.")
+    any(max_bounds .<= min_bounds) && error("max_bounds must be strictly greater than min_bounds for all dimensions.")
+    lo = T.(min_bounds); hi = T.(max_bounds)
+    delta = (hi .- lo) ./ (grid_size .- 1)
+    rho = CUDA.zeros(T, grid_size...)
+    efield = CUDA.zeros(T, grid_size..., 3)
+    return Mesh3D{T, typeof(rho), typeof(efield)}(grid_size, lo, hi, delta, T(gamma), T(total_charge), rho, efield, nothing)
+end
+
+function Base.show(io::IO, mesh::Mesh3D{T}) where {T}
+    nx, ny, nz = mesh.grid_size
+    lo, hi = mesh.min_bounds, mesh.max_bounds
+    print(io, "Mesh3D{$T, CuArray} ($(nx)x$(ny)x$(nz)) bounds=[($(lo[1]),$(lo[2]),$(lo[3])), ($(hi[1]),$(hi[2]),$(hi[3]))] gamma=$(mesh.gamma)")
+end
+
+# ---- clear_mesh!  (src/deposition.jl:10-12) -----------------------------------------------------
+function clear_mesh!(mesh::Mesh3D{T}) where {T}
+    h = handle(mesh)
+    check(h, ccall((:scb_clear, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Int64}, Cint),
+                   h.ptr, mesh.rho, _n(mesh), dtag(T)))
+end
+
+# ---- deposit!  (src/deposition.jl:218-247) -------------------------------------------------------
+function deposit!(mesh::Mesh3D{T}, particles_x, particles_y, particles_z, particles_q; clear::Bool = true) where {T}
+    (length(particles_x) == length(particles_y) == length(particles_z) == length(particles_q)) ||
+        error("Particle coordinate and charge arrays must have the same length.")
+    particles_x isa CuArray || error("Unsupported backend: particle arrays must be CuArrays")
+    P = eltype(particles_x)
+    h = handle(mesh)
+    check(h, ccall((:scb_deposit, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Cint,
+                    Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                   h.ptr, length(particles_x), particles_x, particles_y, particles_z, particles_q, dtag(P), mesh.rho,
+                   dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.delta), clear ? 1 : 0))
+end
+
+# ---- solve! / solve_freespace!  (src/solvers/free_space.jl:14-47, 56-101) -----------------------
+function solve!(mesh::Mesh3D{T}; at_cathode::Bool = false) where {T}
+    h = handle(mesh)
+    check(h, ccall((:scb_solve, LIB), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Float64, Cint),
+                   h.ptr, mesh.rho, mesh.efield, dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.max_bounds),
+                   _f3(mesh.delta), Float64(mesh.gamma), at_cathode ? 1 : 0))
+end
+
+function solve_freespace!(mesh::Mesh3D{T}; offset::NTuple{3, T} = (zero(T), zero(T), zero(T))) where {T}
+    h = handle(mesh)
+    check(h, ccall((:scb_solve_freespace, LIB), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                   h.ptr, mesh.rho, mesh.efield, dtag(T), _n(mesh), _f3(mesh.delta), Float64(mesh.gamma), _f3(offset)))
+end
+
+# ---- interpolate_field  (src/interpolation.jl:100-128) ------------------------------------------
+function interpolate_field(mesh::Mesh3D{T}, particles_x, particles_y, particles_z) where {T}
+    P = eltype(particles_x)
+    Ex = similar(particles_x); Ey = similar(particles_x); Ez = similar(particles_x)
+    h = handle(mesh)
+    check(h, ccall((:scb_interpolate, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Cint, Ptr{Int64},
+                    Ptr{Float64}, Ptr{Float64}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}),
+                   h.ptr, length(particles_x), particles_x, particles_y, particles_z, dtag(P), mesh.efield, dtag(T),
+                   _n(mesh), _f3(mesh.min_bounds), _f3(mesh.delta), Ex, Ey, Ez))
+    return Ex, Ey, Ez
+end
+
+# ---- get_green_function!  (src/green_functions.jl:41-67), parity hook ---------------------------
+"""
+Fills `cgrn` (Complex{T}, size (2nx,2ny,2nz)) like the reference: real part = integrated Green
+function with raw last planes, imaginary part = 0.
+"""
+function get_green_function!(cgrn::CuArray{Complex{T}, 3}, delta::NTuple{3, T}, gamma::T, icomp::Int;
+                             offset::NTuple{3, T} = (zero(T), zero(T), zero(T)), temp = nothing) where {T}
+    re = CUDA.zeros(T, size(cgrn)...)
+    h = default_handle()
+    check(h, ccall((:scb_green, LIB), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Cint),
+                   h.ptr, re, Int64[size(cgrn)...], _f3(delta), Float64(gamma), icomp, _f3(offset), dtag(T)))
+    cgrn .= complex.(re)
+    return cgrn
+end
+
+# src/green_functions.jl:13-22, 35-38 (host-side scalar helpers kept for API completeness)
+@inline function field_green_function(x, y, z)
+    r = sqrt(x^2 + y^2 + z^2)
+    return x * atan((y * z) / (r * x)) - z * log(r + y) + y * log((r - z) / (r + z)) / 2
+end
+
+@inline function potential_green_function(x, y, z)
+    r = sqrt(x^2 + y^2 + z^2)
+    r == zero(x) && return zero(x)
+    half = one(x) / 2
+    return -half * z^2 * atan(x * y / (z * r)) - half * y^2 * atan(x * z / (y * r)) -
+           half * x^2 * atan(y * z / (x * r)) + y * z * log(x + r) + x * z * log(y + r) + x * y * log(z + r)
+end
+
+"""
+    step!(mesh, x, y, z, q, Ex, Ey, Ez; at_cathode=false)
+
+deposit! + solve! + interpolate_field in one call with caller-owned outputs (scb_step).
+"""
+function step!(mesh::Mesh3D{T}, x, y, z, q, Ex, Ey, Ez; at_cathode::Bool = false) where {T}
+    P = eltype(x)
+    h = handle(mesh)
+    check(h, ccall((:scb_step, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid},
+                    CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                    CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}),
+                   h.ptr, length(x), x, y, z, q, dtag(P), mesh.rho, mesh.efield, dtag(T), _n(mesh),
+                   _f3(mesh.min_bounds), _f3(mesh.max_bounds), _f3(mesh.delta), Float64(mesh.gamma), at_cathode ? 1 : 0,
+                   Ex, Ey, Ez))
+end
+
+end # module SpaceChargeB200
