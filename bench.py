@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stages-only", action="store_true", help="print only the per-stage device times (tuning)")
+    ap.add_argument("--replicated-solve", action="store_true", help="multi-GPU: all-reduce rho and solve on every rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +163,9 @@ def main():
         args.workload, npart, grid[0], grid[1], grid[2], ", cathode image" if at_cathode else ""),
         "particles": npart, "grid": list(grid), "at_cathode": at_cathode, "sigma_m": SIGMA,
         "l2": "inputs larger than L2 (particle arrays %.1f GB per step)" % (4 * npart * s / 1e9),
-        "parallelism": "particles sharded over %d GPU(s), rho all-reduced, solve replicated" % world}
+        "parallelism": ("single GPU" if world == 1 else
+                        "particles sharded over %d GPUs; rho reduce-scattered into z slabs, slab-decomposed FFT solve "
+                        "(NCCL all-to-all pencil transposes), E all-gathered" % world)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -202,7 +205,10 @@ def main():
     q = torch.full((n_local,), QTOT / npart, device=dev, dtype=tdt)
     ex, ey, ez = (torch.empty_like(x) for _ in range(3))
 
-    mesh = scb.Mesh3D(grid, x, y, z, T=npdt, total_charge=QTOT, group=group)   # built once, outside the timed region
+    mesh = scb.Mesh3D(grid, x, y, z, T=npdt, total_charge=QTOT, group=group,
+                      sharded_solve=not args.replicated_solve)   # built once, outside the timed region
+    if world > 1 and not mesh.sharded:
+        config["parallelism"] = "particles sharded over %d GPUs, rho all-reduced (NCCL), solve replicated" % world
     hd = mesh.handle
 
     def barrier():
@@ -240,7 +246,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
-    launches = (hd.launch_count() - launches0) + (args.steps if world > 1 else 0)  # + NCCL all-reduce
+    launches = (hd.launch_count() - launches0) + (args.steps if (world > 1 and not mesh.sharded) else 0)  # + NCCL all-reduce
     sampler.stop_flag = True
 
     # per-stage device times (library CUDA events), min over a few extra steps

@@ -140,6 +140,22 @@ SCB_API int scb_step_host(scb_handle* h, int64_t np, const void* x_host, const v
                   const double max_bounds[3], const double delta[3], double gamma,
                   int at_cathode, void* ex_host, void* ey_host, void* ez_host);
 
+/* ---- multi-GPU: particle-sharded step with a slab-decomposed solve (NCCL over NVLink) ------- */
+/* One process and one handle per GPU.  scb_comm_unique_id fills 128 bytes on one rank; the caller
+ * broadcasts them (torch.distributed / MPI) and every rank calls scb_comm_init.  NCCL is dlopen'ed
+ * at that point (libnccl.so.2), so single-GPU users do not need it. */
+SCB_API int scb_comm_unique_id(void* uid128);
+SCB_API int scb_comm_init(scb_handle* h, int nranks, int rank, const void* uid128);
+SCB_API int scb_comm_destroy(scb_handle* h);
+/* rho_partial: this rank's un-reduced charge grid (full size).  Reduce-scatters it into z slabs,
+ * runs the FFT passes slab-decomposed (all-to-all pencil transposes fused into the pass
+ * addressing), and all-gathers the field so that every rank ends with the full efield.
+ * Requires nz and the padded y length to be multiples of nranks; free space or cathode. */
+SCB_API int scb_solve_sharded(scb_handle* h, const void* rho_partial, void* efield, int mdt,
+                              const int64_t n[3], const double min_bounds[3],
+                              const double max_bounds[3], const double delta[3], double gamma,
+                              int at_cathode);
+
 /* ---- cache control ------------------------------------------------------------------------ */
 SCB_API int scb_drop_green_cache(scb_handle* h);
 /* bytes of device workspace currently owned by the handle */

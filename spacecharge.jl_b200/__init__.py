@@ -111,6 +111,28 @@ class Handle:
     def drop_green_cache(self):
         self.check(self.lib.scb_drop_green_cache(self.h))
 
+    def init_comm(self, group):
+        """Create the library's own NCCL communicator for `group` (one rank per GPU): rank 0 draws
+        the unique id, torch.distributed broadcasts it."""
+        import torch
+        import torch.distributed as dist
+        if getattr(self, "_comm_group", None) is group:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            rc = self.lib.scb_comm_unique_id(buf)
+            if rc != 0:
+                raise ScbError(rc, "scb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        dev = "cuda:%d" % self.device if dist.get_backend(group) == "nccl" else "cpu"
+        uid = uid.to(dev)
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0), group=group)
+        raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        self.check(self.lib.scb_comm_init(self.h, world, rank, raw))
+        self._comm_group = group
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
             self.lib.scb_destroy(self.h)
@@ -172,7 +194,7 @@ class Mesh3D:
 
     def __init__(self, grid_size: Sequence[int], *args, T=np.float64, gamma: float = 1.0,
                  total_charge: float = 0.0, device: Optional[int] = None, handle: Optional[Handle] = None,
-                 group=None):
+                 group=None, sharded_solve: bool = True):
         torch = _torch()
         grid_size = tuple(int(g) for g in grid_size)
         if len(grid_size) != 3:
@@ -211,6 +233,17 @@ class Mesh3D:
         self.device = int(device)
         self.handle = handle if handle is not None else default_handle(self.device)
         self.group = group  # torch.distributed process group for particle-sharded runs (or None)
+        # slab-decomposed solve (scb_solve_sharded) when the grid divides over the ranks; otherwise
+        # rho is all-reduced and the solve replicated.  In the sharded mode mesh.rho holds this
+        # rank's PARTIAL charge grid after deposit_ (call reduce_rho_() to materialise the sum).
+        self.sharded = False
+        if group is not None and sharded_solve:
+            import torch.distributed as dist
+            w = dist.get_world_size(group)
+            ly = 8
+            while ly < 2 * grid_size[1]:
+                ly *= 2
+            self.sharded = w > 1 and grid_size[2] % w == 0 and ly % w == 0 and dist.get_backend(group) == "nccl"
         nx, ny, nz = grid_size
         td = _torch_dtype(npdt)
         dev = "cuda:%d" % self.device
@@ -275,6 +308,12 @@ class Mesh3D:
                 % (np.dtype(self.T).name, nx, ny, nz, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], self.gamma))
 
     # helpers for the ABI calls
+    def reduce_rho_(self):
+        """Sum the per-rank partial charge grids in place (sharded mode keeps them partial)."""
+        if self.group is not None:
+            from .sharding import allreduce_rho
+            allreduce_rho(self._rho, self.group)
+
     def _n(self):
         return _lib.i64x3(self.grid_size)
 
@@ -311,7 +350,7 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
         raise ErrorException("particle arrays must share one element type")
     hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
                                 mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
-    if mesh.group is not None:
+    if mesh.group is not None and not mesh.sharded:
         from .sharding import allreduce_rho
         allreduce_rho(mesh._rho, mesh.group)
 
@@ -320,6 +359,11 @@ def solve_(mesh: Mesh3D, at_cathode: bool = False) -> None:
     """solve!  (src/solvers/free_space.jl:14-47)"""
     hd = mesh.handle
     hd.use_current_stream()
+    if mesh.sharded:
+        hd.init_comm(mesh.group)
+        hd.check(hd.lib.scb_solve_sharded(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(),
+                                          mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0))
+        return
     hd.check(hd.lib.scb_solve(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(),
                               mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0))
 

@@ -5,6 +5,9 @@
 #include "fft_passes.cuh"
 #include "kernels.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -66,6 +69,11 @@ struct scb_handle {
     scb_timing last{};
     bool t_dep = false, t_solve = false, t_interp = false, t_green = false, t_pass = false;
     // host-step staging
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    void* slab = nullptr;          // reduce-scattered rho slab
+    size_t slab_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -93,6 +101,51 @@ int cuda_fail(scb_handle* h, cudaError_t e, const char* where) {
     do {                           \
         int rc__ = (expr);         \
         if (rc__ != SCB_OK) return rc__; \
+    } while (0)
+
+struct NcclApi {
+    void* dl = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+bool load_nccl() {
+    if (g_nccl.dl) return true;
+    void* dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) return false;
+#define SCB_SYM(field, name)                                              \
+    *reinterpret_cast<void**>(&g_nccl.field) = dlsym(dl, name);           \
+    if (!g_nccl.field) return false;
+    SCB_SYM(GetUniqueId, "ncclGetUniqueId")
+    SCB_SYM(CommInitRank, "ncclCommInitRank")
+    SCB_SYM(CommDestroy, "ncclCommDestroy")
+    SCB_SYM(ReduceScatter, "ncclReduceScatter")
+    SCB_SYM(AllGather, "ncclAllGather")
+    SCB_SYM(Send, "ncclSend")
+    SCB_SYM(Recv, "ncclRecv")
+    SCB_SYM(GroupStart, "ncclGroupStart")
+    SCB_SYM(GroupEnd, "ncclGroupEnd")
+    SCB_SYM(GetErrorString, "ncclGetErrorString")
+#undef SCB_SYM
+    g_nccl.dl = dl;
+    return true;
+}
+
+#define SCB_NCCL(h, call)                                                                         \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess) return fail(h, SCB_ERR_COMM, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
     } while (0)
 
 int padded_len(int n) {
@@ -446,6 +499,8 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         p.ninner = pl.ninner;
         p.PX = pl.PX;
         p.Ly = pl.L[1];
+        p.Lyg = pl.L[1];
+        p.ky0 = 0;
         if (gfree) {
             p.S = static_cast<const T*>(gfree->data);
             p.S_scomp = gfree->scomp;
@@ -588,6 +643,8 @@ int scb_destroy(scb_handle* h) {
     if (h->arena) cudaFree(h->arena);
     if (h->stage) cudaFree(h->stage);
     if (h->packed) cudaFree(h->packed);
+    if (h->slab) cudaFree(h->slab);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->d_bounds) cudaFree(h->d_bounds);
     if (h->ev_ready)
         for (auto& e : h->ev) cudaEventDestroy(e);
@@ -863,6 +920,194 @@ int64_t scb_workspace_bytes(const scb_handle* h) {
     int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes;
     for (auto& e : h->green) b += (int64_t)e.bytes;
     return b;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// multi-GPU: NCCL is loaded lazily so that the library has no link-time dependency on it
+namespace {
+
+// all-to-all of equal contiguous blocks (block b of `send` goes to rank b; block g of `recv` comes
+// from rank g), `nsets` independent buffers (field components) in one NCCL group
+int all_to_all(scb_handle* h, const char* send, char* recv, size_t block_bytes, int nsets, size_t set_stride_bytes) {
+    SCB_NCCL(h, g_nccl.GroupStart());
+    for (int s = 0; s < nsets; ++s)
+        for (int r = 0; r < h->nranks; ++r) {
+            SCB_NCCL(h, g_nccl.Send(send + s * set_stride_bytes + (size_t)r * block_bytes, block_bytes, ncclChar, r, h->comm, h->stream));
+            SCB_NCCL(h, g_nccl.Recv(recv + s * set_stride_bytes + (size_t)r * block_bytes, block_bytes, ncclChar, r, h->comm, h->stream));
+        }
+    SCB_NCCL(h, g_nccl.GroupEnd());
+    return SCB_OK;
+}
+
+template <typename T>
+int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan& pl, const double delta[3], double gamma,
+                      int mode, const double offset[3]) {
+    using C = cx_t<T>;
+    const int G = h->nranks, me = h->rank;
+    const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
+    const ncclDataType_t nt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+    const int nzl = pl.n[2] / G, Lyl = pl.L[1] / G;
+    const double zero3[3] = {0, 0, 0};
+    const GreenEntry* gfree = nullptr;
+    const GreenEntry* gaux = nullptr;
+    h->t_green = false;
+    SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, zero3, mdt, 0), &gfree));
+    if (mode == 1) {
+        SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 1), &gaux));
+        for (auto& e : h->green)
+            if (e.key == make_key(pl, delta, gamma, zero3, mdt, 0)) gfree = &e;
+    }
+    const size_t slab_elems = (size_t)pl.n[0] * pl.n[1] * nzl;
+    if (h->slab_bytes < slab_elems * sizeof(T)) {
+        if (h->slab) { SCB_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(h->slab); h->slab = nullptr; h->slab_bytes = 0; }
+        if (cudaMalloc(&h->slab, slab_elems * sizeof(T)) != cudaSuccess) { (void)cudaGetLastError(); return fail(h, SCB_ERR_ALLOC, "slab allocation failed"); }
+        h->slab_bytes = slab_elems * sizeof(T);
+    }
+    T* slab = static_cast<T*>(h->slab);
+    const size_t szA = (size_t)pl.PX * pl.n[1] * nzl;       // A_l, D_c
+    const size_t szB = (size_t)pl.PX * pl.L[1] * nzl;       // send/recv buffers (= PX*Lyl*nz)
+    SCB_TRY(ensure_arena(h, (4 * szA + 8 * szB) * sizeof(C)));
+    C* A = static_cast<C*>(h->arena);
+    C* SB = A + szA;          // F2 output, blocked by destination rank
+    C* RB = SB + szB;         // received: [z][ky_l][kx]
+    C* Cc = RB + szB;         // 3 components [z][ky_l][kx]
+    C* R2 = Cc + 3 * szB;     // 3 components, received: [g][z_l][ky_l][kx]
+    C* D = R2 + 3 * szB;      // 3 components [kx][y][z_l]
+    const C *twx, *twy, *twz;
+    SCB_TRY(get_twiddles<T>(h, pl.L[0], &twx));
+    SCB_TRY(get_twiddles<T>(h, pl.L[1], &twy));
+    SCB_TRY(get_twiddles<T>(h, pl.L[2], &twz));
+    const size_t blk = (size_t)pl.PX * Lyl * nzl;           // elements per (rank, rank) block
+
+    tick(h, 8);
+    SCB_NCCL(h, g_nccl.ReduceScatter(rho_partial, slab, slab_elems, nt, ncclSum, h->comm, h->stream));
+    {  // F1 on the slab
+        XParams<T> p{};
+        p.in = slab; p.out = A; p.tw = twx;
+        p.nlines = (long long)pl.n[1] * nzl; p.real_sline = pl.n[0]; p.n_real = pl.n[0]; p.PX = pl.PX; p.scale = (T)1;
+        SCB_CUDA(h, launch_x_r2c<T>(pl.L[0], p, 1, h->stream));
+    }
+    tick(h, 9);
+    {  // F2, output blocked by destination rank: [h][z_l][ky_l][kx]
+        LinesParams<T> p{};
+        p.in = A; p.out = SB; p.tw = twy;
+        p.n_in = pl.n[1]; p.n_out = pl.L[1]; p.ninner = pl.ninner;
+        p.in_sline = pl.PX; p.in_souter = (long long)pl.PX * pl.n[1];
+        p.out_sline = pl.PX; p.out_souter = (long long)pl.PX * Lyl;
+        p.out_split = Lyl; p.out_sblock = (long long)blk;
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], -1, p, nzl, 1, h->stream));
+    }
+    SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(SB), reinterpret_cast<char*>(RB), blk * sizeof(C), 1, 0));
+    tick(h, 10);
+    {  // Z on this rank's ky slab
+        ZParams<T> p{};
+        p.in = RB; p.out = Cc; p.tw = twz;
+        p.out_scomp = (long long)szB;
+        p.nz = pl.n[2]; p.ninner = pl.ninner; p.PX = pl.PX;
+        p.Ly = Lyl; p.Lyg = pl.L[1]; p.ky0 = me * Lyl;
+        p.S = static_cast<const T*>(gfree->data); p.S_scomp = gfree->scomp;
+        if (gaux) { p.H = static_cast<const C*>(gaux->data); p.H_scomp = gaux->scomp; }
+        SCB_CUDA(h, launch_z_fused<T>(pl.L[2], mode == 0 ? GREEN_FREE : GREEN_CATHODE, p, h->stream));
+    }
+    tick(h, 11);
+    SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(Cc), reinterpret_cast<char*>(R2), blk * sizeof(C), 3, szB * sizeof(C)));
+    {  // B2, input blocked by source rank
+        LinesParams<T> p{};
+        p.in = R2; p.out = D; p.tw = twy;
+        p.n_in = pl.L[1]; p.n_out = pl.n[1]; p.ninner = pl.ninner;
+        p.in_sline = pl.PX; p.in_souter = (long long)pl.PX * Lyl;
+        p.in_split = Lyl; p.in_sblock = (long long)blk;
+        p.out_sline = pl.PX; p.out_souter = (long long)pl.PX * pl.n[1];
+        p.in_scomp = (long long)szB; p.out_scomp = (long long)szA;
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, nzl, 3, h->stream));
+    }
+    tick(h, 12);
+    const long long ng = (long long)pl.n[0] * pl.n[1] * pl.n[2];
+    {  // B3 straight into this rank's z slab of the full field
+        XParams<T> p{};
+        p.in = D; p.out = efield + (size_t)me * slab_elems; p.tw = twx;
+        p.nlines = (long long)pl.n[1] * nzl; p.real_sline = pl.n[0]; p.n_real = pl.n[0]; p.PX = pl.PX;
+        p.real_scomp = ng; p.cplx_scomp = (long long)szA;
+        p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
+        SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
+    }
+    SCB_NCCL(h, g_nccl.GroupStart());
+    for (int c = 0; c < 3; ++c)
+        SCB_NCCL(h, g_nccl.AllGather(efield + c * ng + (size_t)me * slab_elems, efield + c * ng, slab_elems, nt, h->comm, h->stream));
+    SCB_NCCL(h, g_nccl.GroupEnd());
+    tick(h, 13);
+    h->t_pass = true;
+    h->launches += 5 + 4;  // five pass kernels + four collectives
+    return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scb_comm_unique_id(void* uid128) {
+    if (!uid128) return SCB_ERR_INVALID_ARG;
+    if (!load_nccl()) return SCB_ERR_COMM;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return SCB_ERR_COMM;
+    std::memcpy(uid128, &id, 128);
+    return SCB_OK;
+}
+
+int scb_comm_init(scb_handle* h, int nranks, int rank, const void* uid128) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!uid128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_comm_init");
+    if (!load_nccl()) return fail(h, SCB_ERR_COMM, "libnccl.so.2 could not be loaded");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, uid128, 128);
+    SCB_NCCL(h, g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->nranks = nranks;
+    h->rank = rank;
+    return SCB_OK;
+}
+
+int scb_comm_destroy(scb_handle* h) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (h->comm) {
+        cudaStreamSynchronize(h->stream);
+        g_nccl.CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->nranks = 1;
+    h->rank = 0;
+    return SCB_OK;
+}
+
+int scb_solve_sharded(scb_handle* h, const void* rho_partial, void* efield, int mdt, const int64_t n[3],
+                      const double min_bounds[3], const double max_bounds[3], const double delta[3], double gamma,
+                      int at_cathode) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!h->comm) return fail(h, SCB_ERR_COMM, "scb_comm_init has not been called");
+    if (!rho_partial || !efield || !delta || !min_bounds || !max_bounds || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_solve_sharded");
+    SCB_TRY(check_grid(h, n));
+    const Plan pl = make_plan(n);
+    if (pl.n[2] % h->nranks != 0 || pl.L[1] % h->nranks != 0)
+        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the padded y length must be multiples of the number of ranks");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    double offset[3] = {0.0, 0.0, 0.0};
+    if (at_cathode) offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
+    tick(h, 2);
+    int rc;
+    if (mdt == SCB_F64)
+        rc = run_solve_sharded<double>(h, (const double*)rho_partial, (double*)efield, pl, delta, gamma, at_cathode ? 1 : 0, offset);
+    else
+        rc = run_solve_sharded<float>(h, (const float*)rho_partial, (float*)efield, pl, delta, gamma, at_cathode ? 1 : 0, offset);
+    tick(h, 3);
+    h->t_solve = rc == SCB_OK;
+    return rc;
 }
 
 }  // extern "C"

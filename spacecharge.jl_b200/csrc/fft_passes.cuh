@@ -52,8 +52,17 @@ struct LinesParams {
     int ninner;         // valid elements along the contiguous axis
     long long in_sline, in_souter, out_sline, out_souter;
     long long in_scomp, out_scomp;  // blockIdx.z selects the field component
+    // slab-decomposed (multi-GPU) runs: the line is cut into blocks of `split` positions, one per
+    // peer rank; position pos lives at (pos % split)*sline + (pos / split)*sblock.  0 = contiguous.
+    int in_split, out_split;
+    long long in_sblock, out_sblock;
     T scale;
 };
+
+template <typename T>
+__device__ __forceinline__ long long line_offset(int pos, long long sline, int split, long long sblock) {
+    return split ? (long long)(pos % split) * sline + (long long)(pos / split) * sblock : (long long)pos * sline;
+}
 
 template <typename T, int N, int DIR>
 __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams<T> p) {
@@ -71,14 +80,16 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
-        v[q] = (valid && pos < p.n_in) ? ld_stream(src + pos * p.in_sline) : cmake<C>(0, 0);
+        v[q] = (valid && pos < p.n_in) ? ld_stream(src + line_offset<T>(pos, p.in_sline, p.in_split, p.in_sblock))
+                                       : cmake<C>(0, 0);
     }
     fft_line<T, N, DIR>(v, lay, j, p.tw);
     C* dst = p.out + (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
-        if (valid && pos < p.n_out) dst[pos * p.out_sline] = cscale(v[q], p.scale);
+        if (valid && pos < p.n_out)
+            dst[line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = cscale(v[q], p.scale);
     }
 }
 
@@ -91,7 +102,8 @@ struct ZParams {
     const cx_t<T>* tw;
     long long out_scomp;
     int nz;                 // valid z planes in and out
-    int ninner, PX, Ly;
+    int ninner, PX, Ly;     // Ly: ky lines held by this rank (= plane pitch / PX)
+    int Lyg, ky0;           // global padded y length and first global ky of this rank (Lyg = Ly, ky0 = 0 on one GPU)
     // GREEN_FREE / GREEN_CATHODE: compressed real spectrum S_c[kx + PXg*(ky' + (Ly/2+1)*kz')],
     // Green_c = i * sign * S_c with ky' = min(ky, Ly-ky), kz' = min(kz, Lz-kz)
     const T* S;
@@ -120,7 +132,8 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tx = threadIdx.x, j = threadIdx.y;
     const int kx = blockIdx.x * TX + tx;
-    const int ky = blockIdx.y;
+    const int kyl = blockIdx.y;        // line within this rank's ky slab
+    const int ky = p.ky0 + kyl;        // global ky: selects the Green-spectrum entries
     const bool valid = kx < p.ninner;
     LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
     // second buffer (cathode only) keeps the forward spectrum so that bin (-kz) can be read
@@ -130,8 +143,8 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
                 (j * TX + tx);
     constexpr int SSTRIDE = TPL * TX;
     const long long plane = (long long)p.PX * p.Ly;
-    const int Lyh = p.Ly / 2;
-    const int kyf = ky <= Lyh ? ky : p.Ly - ky;  // folded ky
+    const int Lyh = p.Lyg / 2;
+    const int kyf = ky <= Lyh ? ky : p.Lyg - ky;  // folded ky
 
     auto prefetch_S = [&](int c) {
         if constexpr (USE_S) {
@@ -151,7 +164,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
     prefetch_S(0);
     C spec[8];
     {
-        const C* src = p.in + (long long)ky * p.PX + kx;
+        const C* src = p.in + (long long)kyl * p.PX + kx;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int pos = j + q * TPL;
@@ -182,12 +195,12 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
                     acc = cmake<C>(-spec[q].y * s, spec[q].x * s);
                 }
                 if constexpr (KIND == GREEN_CATHODE) {
-                    const C h = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Ly * kz));
+                    const C h = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Lyg * kz));
                     const C m = laym.ld((N - kz) & (N - 1));
                     acc = cadd(acc, cmul(m, h));
                 }
                 if constexpr (KIND == GREEN_FULL) {
-                    const C g = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Ly * kz));
+                    const C g = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Lyg * kz));
                     acc = cmul(spec[q], g);
                 }
             }
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
         }
         if (c < 2) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
         fft_line<T, N, +1>(w, lay, j, p.tw);
-        C* dst = p.out + c * p.out_scomp + (long long)ky * p.PX + kx;
+        C* dst = p.out + c * p.out_scomp + (long long)kyl * p.PX + kx;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int pos = j + q * TPL;
