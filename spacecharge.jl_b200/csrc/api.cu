@@ -10,6 +10,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -42,6 +43,7 @@ struct GreenEntry {
     GreenKey key;
     void* data = nullptr;
     size_t bytes = 0;
+    size_t cap = 0;       // allocated size (>= bytes when the buffer was recycled)
     long long scomp = 0;
     unsigned long long stamp = 0;
 };
@@ -57,6 +59,7 @@ struct scb_handle {
     size_t arena_bytes = 0;
     std::map<std::pair<int, int>, void*> twiddles;  // (N, is_f64) -> device table of N roots
     std::vector<GreenEntry> green;
+    std::vector<std::pair<void*, size_t>> green_pool;  // retired spectrum buffers, reused by the next build
     unsigned long long stamp = 0;
     unsigned long long* d_bounds = nullptr;
     void* packed = nullptr;       // node-major copy of efield for the gather (32 bytes per node)
@@ -291,25 +294,46 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     const size_t nG = (size_t)pl.L[0] * pl.L[1] * pl.L[2];
     const size_t nS = (size_t)pl.PX * pl.L[1] * pl.L[2];
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t need = al(nP * 8) + al(nG * 8) + al(nS * 16);
+    // free space: only ky <= Ly/2 and kz <= Lz/2 are kept, so the y pass prunes its output and the
+    // z pass runs on half of the lines
+    const int Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
+    const bool prune = key.kind == 0;
+    const size_t nY2 = prune ? (size_t)pl.PX * Lyh1 * pl.L[2] : 0;
+    const size_t need = 2 * al(nP * 8) + al(nG * 8) + al(nS * 16) + al(nY2 * 16);
     SCB_TRY(ensure_arena(h, need));
     char* base = static_cast<char*>(h->arena);
     double* P = reinterpret_cast<double*>(base);
-    double* G = reinterpret_cast<double*>(base + al(nP * 8));
-    double2* spec = reinterpret_cast<double2*>(base + al(nP * 8) + al(nG * 8));
+    double* Dd = reinterpret_cast<double*>(base + al(nP * 8));
+    double* G = reinterpret_cast<double*>(base + 2 * al(nP * 8));
+    double2* spec = reinterpret_cast<double2*>(base + 2 * al(nP * 8) + al(nG * 8));
+    double2* Y2 = reinterpret_cast<double2*>(base + 2 * al(nP * 8) + al(nG * 8) + al(nS * 16));
 
     const bool f64 = key.mdt == SCB_F64;
     size_t per_comp;  // elements
-    if (key.kind == 0) per_comp = (size_t)pl.PX * (pl.L[1] / 2 + 1) * (pl.L[2] / 2 + 1);
+    if (key.kind == 0) per_comp = (size_t)pl.PX * Lyh1 * Lzh1;
     else per_comp = nS;
     const size_t elem = (key.kind == 0 ? 1 : 2) * dt_size(key.mdt);
     ent.bytes = 3 * per_comp * elem;
     ent.scomp = (long long)per_comp;
-    cudaError_t e = cudaMalloc(&ent.data, ent.bytes);
-    if (e != cudaSuccess) {
-        (void)cudaGetLastError();
-        ent.data = nullptr;
-        return fail(h, SCB_ERR_ALLOC, "Green-spectrum allocation failed");
+    // reuse a retired buffer when one is large enough: cudaFree/cudaMalloc of ~0.5 GB blocks costs
+    // anything from 1 to 400 ms on the host and would dominate a re-mesh-every-step workload
+    ent.data = nullptr;
+    for (size_t i = 0; i < h->green_pool.size(); ++i) {
+        if (h->green_pool[i].second >= ent.bytes && h->green_pool[i].second <= 2 * ent.bytes) {
+            ent.data = h->green_pool[i].first;
+            ent.cap = h->green_pool[i].second;
+            h->green_pool.erase(h->green_pool.begin() + i);
+            break;
+        }
+    }
+    if (!ent.data) {
+        cudaError_t e = cudaMalloc(&ent.data, ent.bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ent.data = nullptr;
+            return fail(h, SCB_ERR_ALLOC, "Green-spectrum allocation failed");
+        }
+        ent.cap = ent.bytes;
     }
 
     const double2 *twx, *twy, *twz;
@@ -319,7 +343,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
 
     for (int c = 0; c < 3; ++c) {
         SCB_CUDA(h, launch_green_point(P, g, c + 1, h->stream));
-        SCB_CUDA(h, launch_green_place(G, P, g, c + 1, sign_all, h->stream));
+        SCB_CUDA(h, launch_green_place(G, Dd, P, g, c + 1, sign_all, h->stream));
         XParams<double> xp{};
         xp.in = G;
         xp.out = spec;
@@ -330,40 +354,59 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         xp.PX = pl.PX;
         xp.scale = 1.0;
         SCB_CUDA(h, launch_x_r2c<double>(pl.L[0], xp, 1, h->stream));
+        const int ly_out = prune ? Lyh1 : pl.L[1];   // ky kept after the y pass
+        const int lz_out = prune ? Lzh1 : pl.L[2];
+        double2* ydst = prune ? Y2 : spec;
+        double2* zdst = spec;                        // pruned: [kx][ky<=Ly/2][kz<=Lz/2]; else in place
         LinesParams<double> yp{};
         yp.in = spec;
-        yp.out = spec;
+        yp.out = ydst;
         yp.tw = twy;
-        yp.n_in = yp.n_out = pl.L[1];
+        yp.n_in = pl.L[1];
+        yp.n_out = ly_out;
         yp.ninner = pl.ninner;
         yp.in_sline = yp.out_sline = pl.PX;
-        yp.in_souter = yp.out_souter = (long long)pl.PX * pl.L[1];
+        yp.in_souter = (long long)pl.PX * pl.L[1];
+        yp.out_souter = (long long)pl.PX * ly_out;
         yp.scale = 1.0;
         SCB_CUDA(h, launch_lines<double>(pl.L[1], -1, yp, pl.L[2], 1, h->stream));
         LinesParams<double> zp{};
-        zp.in = spec;
-        zp.out = spec;
+        zp.in = ydst;
+        zp.out = zdst;
         zp.tw = twz;
-        zp.n_in = zp.n_out = pl.L[2];
+        zp.n_in = pl.L[2];
+        zp.n_out = lz_out;
         zp.ninner = pl.ninner;
-        zp.in_sline = zp.out_sline = (long long)pl.PX * pl.L[1];
+        zp.in_sline = zp.out_sline = (long long)pl.PX * ly_out;
         zp.in_souter = zp.out_souter = pl.PX;
         zp.scale = 1.0;
-        SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, pl.L[1], 1, h->stream));
+        SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, ly_out, 1, h->stream));
         char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
         if (key.kind == 0)
-            SCB_CUDA(h, launch_green_compress_free(dst, f64, spec, pl.ninner, pl.PX, pl.L[1], pl.L[2], h->stream));
+            SCB_CUDA(h, launch_green_compress_free(dst, f64, spec, pl.ninner, pl.PX, Lyh1, Lzh1, h->stream));
         else
             SCB_CUDA(h, launch_green_convert_full(dst, f64, spec, pl.ninner, pl.PX, (long long)nS, h->stream));
-        h->launches += 6;
+        h->launches += 7;
     }
     return SCB_OK;
 }
 
-void free_green(scb_handle* h) {
-    for (auto& e : h->green)
-        if (e.data) cudaFree(e.data);
+// stream-ordered reuse is safe: every consumer of a retired buffer was enqueued on h->stream before
+// the next build's kernels
+void retire_green(scb_handle* h, GreenEntry& e) {
+    if (!e.data) return;
+    if (h->green_pool.size() < 4) h->green_pool.push_back({e.data, e.cap});
+    else cudaFree(e.data);
+    e.data = nullptr;
+}
+
+void free_green(scb_handle* h, bool release_pool) {
+    for (auto& e : h->green) retire_green(h, e);
     h->green.clear();
+    if (release_pool) {
+        for (auto& b : h->green_pool) cudaFree(b.first);
+        h->green_pool.clear();
+    }
 }
 
 int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEntry** out) {
@@ -379,8 +422,7 @@ int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEnt
         // reference behaviour: the Green function is recomputed on every solve
         for (size_t i = 0; i < h->green.size();) {
             if (h->green[i].key.kind == key.kind) {
-                SCB_CUDA(h, cudaStreamSynchronize(h->stream));
-                cudaFree(h->green[i].data);
+                retire_green(h, h->green[i]);
                 h->green.erase(h->green.begin() + i);
             } else {
                 ++i;
@@ -391,8 +433,7 @@ int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEnt
         size_t victim = 0;
         for (size_t i = 1; i < h->green.size(); ++i)
             if (h->green[i].stamp < h->green[victim].stamp) victim = i;
-        SCB_CUDA(h, cudaStreamSynchronize(h->stream));
-        cudaFree(h->green[victim].data);
+        retire_green(h, h->green[victim]);
         h->green.erase(h->green.begin() + victim);
     }
     GreenEntry ent;
@@ -403,7 +444,7 @@ int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEnt
     tick(h, 7);
     h->t_green = true;
     if (rc != SCB_OK) {
-        if (ent.data) cudaFree(ent.data);
+        retire_green(h, ent);
         return rc;
     }
     h->green.push_back(ent);
@@ -622,6 +663,7 @@ int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->opt.green_cache = 1;
     if (opt) h->opt = *opt;
+    if (const char* e = std::getenv("SCB_DEPOSIT_MODE")) h->opt.deposit_mode = std::atoi(e);  // tuning knob
     if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
         return SCB_ERR_ALLOC;
@@ -638,7 +680,7 @@ int scb_destroy(scb_handle* h) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
     }
-    free_green(h);
+    free_green(h, true);
     for (auto& kv : h->twiddles) cudaFree(kv.second);
     if (h->arena) cudaFree(h->arena);
     if (h->stage) cudaFree(h->stage);
@@ -720,7 +762,7 @@ int scb_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const v
     SCB_CUDA(h, cudaSetDevice(h->device));
     tick(h, 0);
     if (clear) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
-    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, make_geom(n, min_bounds, delta), h->stream));
+    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, make_geom(n, min_bounds, delta), h->opt.deposit_mode, h->stream));
     tick(h, 1);
     h->t_dep = true;
     if (np > 0) h->launches += 1;
@@ -877,7 +919,7 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
             SCB_CUDA(h, cudaMemcpyAsync(d[a] + o * es, (const char*)src[a] + o * es, m * es, cudaMemcpyHostToDevice, h->copy_stream));
         SCB_CUDA(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
         SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
-        SCB_CUDA(h, launch_deposit(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, d[3] + o * es, rho, g, h->stream));
+        SCB_CUDA(h, launch_deposit(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, d[3] + o * es, rho, g, h->opt.deposit_mode, h->stream));
         h->launches += 1;
     }
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
@@ -910,15 +952,15 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
 
 int scb_drop_green_cache(scb_handle* h) {
     if (!h) return SCB_ERR_INVALID_ARG;
-    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
-    free_green(h);
+    free_green(h, false);
     return SCB_OK;
 }
 
 int64_t scb_workspace_bytes(const scb_handle* h) {
     if (!h) return 0;
     int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes;
-    for (auto& e : h->green) b += (int64_t)e.bytes;
+    for (auto& e : h->green) b += (int64_t)e.cap;
+    for (auto& e : h->green_pool) b += (int64_t)e.second;
     return b;
 }
 

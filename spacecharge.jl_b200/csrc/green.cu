@@ -67,10 +67,22 @@ __global__ void k_green_reference_layout(TO* __restrict__ out, const double* __r
     out[idx] = (TO)v;
 }
 
-// Differencing fused with placement into the padded real array g[X + Lx*(Y + Ly*Z)].
+// 8-point differencing on the stored corner ranges: D[a + dcx*(b + dcy*c)] = IGF for the cell whose
+// lower corner is (a,b,c); one value per distinct displacement (an octant for symmetric axes).
+__global__ void k_green_diff(double* __restrict__ D, const double* __restrict__ P, IgfGeom g) {
+    const int dcx = g.cnt[0] - 1, dcy = g.cnt[1] - 1, dcz = g.cnt[2] - 1;
+    const long long total = (long long)dcx * dcy * dcz;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int a = (int)(idx % dcx), b = (int)((idx / dcx) % dcy), c = (int)(idx / ((long long)dcx * dcy));
+    D[idx] = diff8(P, g.cnt[0], g.cnt[1], a, b, c);
+}
+
+// Placement of the differenced values into the padded real array g[X + Lx*(Y + Ly*Z)].
 // axis modes: conv = wrap-around placement of displacement d at index d mod L;
 //             corr = displacement d at index d + (n-1) (image charge along z).
-__global__ void k_green_place(double* __restrict__ gout, const double* __restrict__ P, IgfGeom g, int icomp, double sign_all) {
+// Symmetric axes read |d| and flip the sign when the axis is the component's own (odd) axis.
+__global__ void k_green_place(double* __restrict__ gout, const double* __restrict__ D, IgfGeom g, int icomp, double sign_all) {
     const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -100,21 +112,19 @@ __global__ void k_green_place(double* __restrict__ gout, const double* __restric
             m0[a] = d + n - 1;
         }
     }
-    gout[idx] = zero ? 0.0 : sgn * diff8(P, g.cnt[0], g.cnt[1], m0[0], m0[1], m0[2]);
+    const int dcx = g.cnt[0] - 1, dcy = g.cnt[1] - 1;
+    gout[idx] = zero ? 0.0 : sgn * __ldg(D + m0[0] + (long long)dcx * (m0[1] + (long long)dcy * m0[2]));
 }
 
 // Spectrum -> cached forms.
-// free space: Green_c = i*S_c, S_c real, kept for kx<=Lx/2, ky<=Ly/2, kz<=Lz/2
+// free space: Green_c = i*S_c, S_c real; the passes already pruned the spectrum to kx<=Lx/2,
+// ky<=Ly/2, kz<=Lz/2 (layout [kx][ky][kz], pitch PX), so this only takes the imaginary part
 template <typename T>
-__global__ void k_green_compress_free(T* __restrict__ S, const double2* __restrict__ spec, int ninner, int PX, int Ly, int Lz) {
-    const int Lyh = Ly / 2 + 1, Lzh = Lz / 2 + 1;
-    const long long total = (long long)PX * Lyh * Lzh;
+__global__ void k_green_compress_free(T* __restrict__ S, const double2* __restrict__ spec, int ninner, int PX, long long total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int kx = (int)(idx % PX), ky = (int)((idx / PX) % Lyh), kz = (int)(idx / ((long long)PX * Lyh));
-    T v = (T)0;
-    if (kx < ninner) v = (T)spec[kx + (long long)PX * (ky + (long long)Ly * kz)].y;
-    S[idx] = v;
+    const int kx = (int)(idx % PX);
+    S[idx] = kx < ninner ? (T)spec[idx].y : (T)0;
 }
 
 template <typename T>
@@ -142,16 +152,18 @@ cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P
     return cudaGetLastError();
 }
 
-cudaError_t launch_green_place(double* gout, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s) {
+cudaError_t launch_green_place(double* gout, double* D, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s) {
+    const long long nd = (long long)(g.cnt[0] - 1) * (g.cnt[1] - 1) * (g.cnt[2] - 1);
+    k_green_diff<<<blocks_for(nd, 256), 256, 0, s>>>(D, P, g);
     const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
-    k_green_place<<<blocks_for(total, 256), 256, 0, s>>>(gout, P, g, icomp, sign_all);
+    k_green_place<<<blocks_for(total, 256), 256, 0, s>>>(gout, D, g, icomp, sign_all);
     return cudaGetLastError();
 }
 
-cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Ly, int Lz, cudaStream_t s) {
-    const long long total = (long long)PX * (Ly / 2 + 1) * (Lz / 2 + 1);
-    if (dt_f64) k_green_compress_free<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)S, spec, ninner, PX, Ly, Lz);
-    else k_green_compress_free<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, ninner, PX, Ly, Lz);
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1, cudaStream_t s) {
+    const long long total = (long long)PX * Lyh1 * Lzh1;
+    if (dt_f64) k_green_compress_free<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)S, spec, ninner, PX, total);
+    else k_green_compress_free<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, ninner, PX, total);
     return cudaGetLastError();
 }
 

@@ -26,13 +26,15 @@ struct Geom3 {
 // green.cu
 cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStream_t s);
 cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s);
-cudaError_t launch_green_place(double* gout, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s);
-cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Ly, int Lz, cudaStream_t s);
+// D: scratch for the differenced values, (cnt-1)^3 doubles
+cudaError_t launch_green_place(double* gout, double* D, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s);
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1, cudaStream_t s);
 cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, int ninner, int PX, long long total, cudaStream_t s);
 
 // particles.cu  (pdt/mdt: 0 = f32, 1 = f64)
+// mode 1: one thread per particle; otherwise eight lanes per particle (x-neighbours coalesce in L2)
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                           const void* q, void* rho, const Geom3& g, cudaStream_t s);
+                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
 // node-major repack of efield (32 bytes per node) and the gather that reads it

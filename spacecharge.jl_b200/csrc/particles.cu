@@ -10,6 +10,8 @@
 // out-of-bounds write the reference performs for Float32 auto-bounds meshes.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace scb {
 
 template <typename P, typename T> struct promote { using type = double; };
@@ -58,6 +60,52 @@ __global__ void __launch_bounds__(256) k_deposit(long long np, const P* __restri
         atomicAdd(r + sz + 1, (T)(charge * wx1 * wy0 * wz1));
         atomicAdd(r + sz + sy, (T)(charge * wx0 * wy1 * wz1));
         atomicAdd(r + sz + sy + 1, (T)(charge * wx1 * wy1 * wz1));
+    }
+}
+
+// ---- deposit, lane-cooperative variant -------------------------------------------------------
+// ncu (round 1) shows the kernel above bound by the L2 reduction path (lts 84 %, dram 10 %).  A
+// warp instruction's lanes that hit the same 32-byte sector travel to L2 as one request, but the
+// eight reductions of one particle are eight instructions.  Here eight lanes share a particle
+// (lane & 7 = corner, bit 0 = x), so the two x-neighbours of every corner pair sit in adjacent
+// lanes of ONE reduction instruction and usually in one sector.  Each lane forms its corner's
+// value with the reference's expression charge*wx*wy*wz, so per-contribution values are
+// bit-identical to k_deposit; only the (already unordered) accumulation order differs.
+template <typename P, typename T>
+__global__ void __launch_bounds__(256) k_deposit_coop(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                       const P* __restrict__ z, const P* __restrict__ q,
+                                                       T* __restrict__ rho, const Geom3 g) {
+    using W = typename promote<P, T>::type;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const int k = lane & 7;
+    const long long koff = (k & 1) + ((k >> 1) & 1) * sy + ((k >> 2) & 1) * sz;
+    for (long long base = warp * 32; base < np; base += nwarps * 32) {
+        const long long i = base + lane;
+        W f0 = 0, f1 = 0, f2 = 0, charge = 0;
+        long long off = 0;
+        if (i < np) {
+            CellW<W> c;
+            locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+            charge = (W)ld_stream(q + i);
+            f0 = c.f[0]; f1 = c.f[1]; f2 = c.f[2];
+            off = c.i[0] + sy * c.i[1] + sz * c.i[2];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int src = 4 * r + (lane >> 3);
+            const W fx = __shfl_sync(0xffffffffu, f0, src);
+            const W fy = __shfl_sync(0xffffffffu, f1, src);
+            const W fz = __shfl_sync(0xffffffffu, f2, src);
+            const W qq = __shfl_sync(0xffffffffu, charge, src);
+            const long long o = __shfl_sync(0xffffffffu, off, src);
+            const W wx = (k & 1) ? fx : (W)1 - fx;
+            const W wy = (k & 2) ? fy : (W)1 - fy;
+            const W wz = (k & 4) ? fz : (W)1 - fz;
+            if (base + src < np) atomicAdd(rho + o + koff, (T)(qq * wx * wy * wz));
+        }
     }
 }
 
@@ -177,6 +225,74 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f64(long long np, co
     }
 }
 
+// Lane-pair variant for Float64 fields: ncu (round 1) shows the kernel above limited by L1 tag
+// look-ups (one 128-byte line per lane per load, l1tex 92 %) before L2 (74 %).  Two adjacent lanes
+// share a particle, lane&1 selects the x corner, so both x-neighbours of a (y,z) corner are
+// fetched by ONE load instruction from (usually) one line.  Each lane forms the reference's
+// weights (1-dx)*(1-dy)*(1-dz) ... and products; the eight products are summed as
+// (p000+p010+p001+p011) + (p100+p110+p101+p111), i.e. in a different order than the reference's
+// left-to-right sum (last-ulp differences, well inside the 1e-10 parity bar).
+template <typename P>
+__global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, const P* __restrict__ x,
+                                                               const P* __restrict__ y, const P* __restrict__ z,
+                                                               const double4* __restrict__ e, const Geom3 g,
+                                                               P* __restrict__ ex, P* __restrict__ ey,
+                                                               P* __restrict__ ez) {
+    using W = double;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const int kx = lane & 1;
+    for (long long base = warp * 32; base < np; base += nwarps * 32) {
+        const long long i = base + lane;
+        W f0 = 0, f1 = 0, f2 = 0;
+        long long off = 0;
+        if (i < np) {
+            CellW<W> c;
+            locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+            f0 = c.f[0]; f1 = c.f[1]; f2 = c.f[2];
+            off = c.i[0] + sy * c.i[1] + sz * c.i[2];
+        }
+        W mine[3] = {0, 0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int src = 16 * h + (lane >> 1);
+            const W dx = __shfl_sync(FULL, f0, src);
+            const W dy = __shfl_sync(FULL, f1, src);
+            const W dz = __shfl_sync(FULL, f2, src);
+            const long long o = __shfl_sync(FULL, off, src);
+            const double4* b = e + o + kx;
+            double n00[4], n10[4], n01[4], n11[4];   // (y,z), (y+1,z), (y,z+1), (y+1,z+1) at this lane's x corner
+            ld256(b, n00);
+            ld256(b + sy, n10);
+            ld256(b + sz, n01);
+            ld256(b + sz + sy, n11);
+            const W one = 1.0;
+            const W wx = kx ? dx : one - dx;
+            const W w00 = wx * (one - dy) * (one - dz);
+            const W w10 = wx * dy * (one - dz);
+            const W w01 = wx * (one - dy) * dz;
+            const W w11 = wx * dy * dz;
+            W acc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[k] = n00[k] * w00 + n10[k] * w10 + n01[k] * w01 + n11[k] * w11;
+                const W other = __shfl_xor_sync(FULL, acc[k], 1);
+                acc[k] = kx ? other + acc[k] : acc[k] + other;   // x0 part + x1 part on both lanes
+                const W got = __shfl_sync(FULL, acc[k], 2 * (lane & 15));
+                if ((lane >> 4) == h) mine[k] = got;
+            }
+        }
+        if (i < np) {
+            st_stream(ex + i, (P)mine[0]);
+            st_stream(ey + i, (P)mine[1]);
+            st_stream(ez + i, (P)mine[2]);
+        }
+    }
+}
+
 template <typename P>
 __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, const P* __restrict__ x,
                                                                  const P* __restrict__ y, const P* __restrict__ z,
@@ -283,12 +399,18 @@ static inline unsigned particle_grid(long long np, int bs, int per_sm) {
     else { CALL(double, double) }
 
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                           const void* q, void* rho, const Geom3& g, cudaStream_t s) {
+                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
+    if (mode == 1) {
 #define CALL(P, T) k_deposit<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
-    SCB_DISPATCH_PT(CALL)
+        SCB_DISPATCH_PT(CALL)
 #undef CALL
+    } else {
+#define CALL(P, T) k_deposit_coop<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
+        SCB_DISPATCH_PT(CALL)
+#undef CALL
+    }
     return cudaGetLastError();
 }
 
@@ -314,9 +436,13 @@ cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void
                                       const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
-    if (mdt == 1) {
+    static const bool thread_per_particle = [] { const char* e = getenv("SCB_INTERP_MODE"); return e && atoi(e) == 1; }();
+    if (mdt == 1 && thread_per_particle) {
         if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
         else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
+    } else if (mdt == 1) {
+        if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
+        else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
     } else {
         if (pdt == 1) k_interpolate_packed_f32<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
         else k_interpolate_packed_f32<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
