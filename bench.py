@@ -65,36 +65,58 @@ def algorithmic_bytes(npart, grid, s, at_cathode):
 
 
 class ClockSampler(threading.Thread):
+    """One persistent `nvidia-smi -lms 100` process (a fresh nvidia-smi per sample takes ~1 s, longer
+    than the timed region); samples are time-stamped and the summary uses those taken between
+    mark_begin() and mark_end(), i.e. while the GPU is under the benchmark's load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
+        self.t_begin, self.t_end = None, None
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                cells = [c.strip() for c in line.split(",")]
+                if len(cells) >= 8:
+                    self.rows.append((time.time(), cells))
+        except Exception:
+            pass
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def stop(self):
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
 
     def summary(self):
-        if not self.rows:
+        rows = [c for (t, c) in self.rows
+                if self.t_begin is None or (self.t_begin - 0.05 <= t <= (self.t_end or t) + 0.15)]
+        if not rows:
+            rows = [c for (_, c) in self.rows]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows)
+        sm = sorted(float(r[1]) for r in rows)
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]),
-                "power_w_max": max(float(r[3]) for r in self.rows), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=150.0):
@@ -218,7 +240,9 @@ def main():
 
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.stages_only:
-        sampler.start()   # samples through warm-up and the timed region (the region itself lasts ~0.1 s)
+        sampler.start()
+        time.sleep(1.0)   # let nvidia-smi start streaming before the load begins
+    sampler.mark_begin()  # warm-up + timed region = the loaded interval that is sampled
     for _ in range(max(args.warmup, 3)):
         scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
     barrier()
@@ -246,8 +270,10 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
+    sampler.mark_end()
     launches = (hd.launch_count() - launches0) + (args.steps if (world > 1 and not mesh.sharded) else 0)  # + NCCL all-reduce
-    sampler.stop_flag = True
+    time.sleep(0.15)
+    sampler.stop()
 
     # per-stage device times (library CUDA events), min over a few extra steps
     hd.enable_timing(True)
@@ -276,7 +302,8 @@ def main():
         gbs = ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0
         stage_roof[k] = {"ms": round(stage[k], 4), "alg_MB": round(ab[k] / 1e6, 1), "GBps": round(gbs, 1),
                          "frac": round(gbs / peak, 4)}
-    kernel_names = {"deposit": "k_deposit", "interpolate": "k_interpolate", "F1": "k_x_r2c", "F2": "k_lines<-1>",
+    kernel_names = {"deposit": "k_deposit_pair", "interpolate": "k_interpolate_pair_f64" if s == 8 else "k_interpolate_packed_f32",
+                    "F1": "k_x_r2c", "F2": "k_lines<-1>",
                     "Z": "k_z_fused", "B2": "k_lines<+1>", "B3": "k_x_c2r"}
     dom = max(stage_roof, key=lambda k: stage_roof[k]["ms"])
     roofline = {"kernel": kernel_names[dom], "stage": dom, "bound": "hbm", "achieved": stage_roof[dom]["GBps"],

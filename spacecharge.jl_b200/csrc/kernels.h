@@ -32,7 +32,7 @@ cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec,
 cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, int ninner, int PX, long long total, cudaStream_t s);
 
 // particles.cu  (pdt/mdt: 0 = f32, 1 = f64)
-// mode 1: one thread per particle; otherwise eight lanes per particle (x-neighbours coalesce in L2)
+// mode 1: one thread per particle; otherwise two lanes per particle (x-neighbours coalesce in L2)
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                            const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,

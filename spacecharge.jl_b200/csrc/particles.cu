@@ -63,25 +63,28 @@ __global__ void __launch_bounds__(256) k_deposit(long long np, const P* __restri
     }
 }
 
-// ---- deposit, lane-cooperative variant -------------------------------------------------------
-// ncu (round 1) shows the kernel above bound by the L2 reduction path (lts 84 %, dram 10 %).  A
-// warp instruction's lanes that hit the same 32-byte sector travel to L2 as one request, but the
-// eight reductions of one particle are eight instructions.  Here eight lanes share a particle
-// (lane & 7 = corner, bit 0 = x), so the two x-neighbours of every corner pair sit in adjacent
-// lanes of ONE reduction instruction and usually in one sector.  Each lane forms its corner's
-// value with the reference's expression charge*wx*wy*wz, so per-contribution values are
-// bit-identical to k_deposit; only the (already unordered) accumulation order differs.
+// ---- deposit, lane-pair variant ----------------------------------------------------------------
+// ncu (round 1) shows the kernel above bound by the L2 reduction path (lts 84 %, dram 10 %): every
+// reduction is its own 32-byte sector transaction.  A warp instruction's lanes that hit the same
+// sector travel to L2 as ONE transaction, but the eight reductions of a particle are eight
+// instructions.  Here two adjacent lanes share a particle (lane & 1 = x corner), so the two
+// x-neighbours of every (y,z) corner pair go out in one reduction instruction and usually in one
+// sector: 5 instead of 8 sector transactions per particle (measured: l1tex red sectors 5.0e8 for
+// 1e8 particles).  Each lane forms its corners' values with the reference's expression
+// ((q*wx)*wy)*wz, so the per-contribution values are bit-identical to k_deposit; only the (already
+// unordered) accumulation order differs.  (An eight-lanes-per-particle version had the same
+// sector count but spent a third of the LSU pipe on shuffles.)
 template <typename P, typename T>
-__global__ void __launch_bounds__(256) k_deposit_coop(long long np, const P* __restrict__ x, const P* __restrict__ y,
+__global__ void __launch_bounds__(256) k_deposit_pair(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                        const P* __restrict__ z, const P* __restrict__ q,
                                                        T* __restrict__ rho, const Geom3 g) {
     using W = typename promote<P, T>::type;
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
-    const int k = lane & 7;
-    const long long koff = (k & 1) + ((k >> 1) & 1) * sy + ((k >> 2) & 1) * sz;
+    const int kx = lane & 1;
     for (long long base = warp * 32; base < np; base += nwarps * 32) {
         const long long i = base + lane;
         W f0 = 0, f1 = 0, f2 = 0, charge = 0;
@@ -94,17 +97,23 @@ __global__ void __launch_bounds__(256) k_deposit_coop(long long np, const P* __r
             off = c.i[0] + sy * c.i[1] + sz * c.i[2];
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int src = 4 * r + (lane >> 3);
-            const W fx = __shfl_sync(0xffffffffu, f0, src);
-            const W fy = __shfl_sync(0xffffffffu, f1, src);
-            const W fz = __shfl_sync(0xffffffffu, f2, src);
-            const W qq = __shfl_sync(0xffffffffu, charge, src);
-            const long long o = __shfl_sync(0xffffffffu, off, src);
-            const W wx = (k & 1) ? fx : (W)1 - fx;
-            const W wy = (k & 2) ? fy : (W)1 - fy;
-            const W wz = (k & 4) ? fz : (W)1 - fz;
-            if (base + src < np) atomicAdd(rho + o + koff, (T)(qq * wx * wy * wz));
+        for (int h = 0; h < 2; ++h) {
+            const int src = 16 * h + (lane >> 1);
+            const W fx = __shfl_sync(FULL, f0, src);
+            const W fy = __shfl_sync(FULL, f1, src);
+            const W fz = __shfl_sync(FULL, f2, src);
+            const W qq = __shfl_sync(FULL, charge, src);
+            const long long o = __shfl_sync(FULL, off, src);
+            if (base + src < np) {
+                const W one = (W)1;
+                const W qx = qq * (kx ? fx : one - fx);        // charge * w_x
+                const W qxy0 = qx * (one - fy), qxy1 = qx * fy;  // * w_y
+                T* r = rho + o + kx;
+                atomicAdd(r, (T)(qxy0 * (one - fz)));
+                atomicAdd(r + sy, (T)(qxy1 * (one - fz)));
+                atomicAdd(r + sz, (T)(qxy0 * fz));
+                atomicAdd(r + sz + sy, (T)(qxy1 * fz));
+            }
         }
     }
 }
@@ -407,7 +416,7 @@ cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const 
         SCB_DISPATCH_PT(CALL)
 #undef CALL
     } else {
-#define CALL(P, T) k_deposit_coop<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
+#define CALL(P, T) k_deposit_pair<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
         SCB_DISPATCH_PT(CALL)
 #undef CALL
     }
