@@ -22,17 +22,24 @@
 namespace scb {
 
 // threads that advance in lockstep along the contiguous axis in the strided passes
+#ifndef SCB_LTX_BIG
+#define SCB_LTX_BIG 8
+#endif
 __host__ __device__ constexpr int tx_for(int N) {
-    return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? 8 : N == 128 ? 16 : 32;
+    return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? SCB_LTX_BIG : N == 128 ? 16 : 32;
 }
 // lockstep lines of the fused z pass (its register footprint is twice that of a plain pass, so
 // it runs narrower CTAs to keep two of them resident per SM)
 #ifndef SCB_ZTX_BIG
-#define SCB_ZTX_BIG 8
+#define SCB_ZTX_BIG 4
 #endif
 #ifndef SCB_Z_MINBLOCKS
-#define SCB_Z_MINBLOCKS 1
+#define SCB_Z_MINBLOCKS 2
 #endif
+#ifndef SCB_Z_MINBLOCKS_F32
+#define SCB_Z_MINBLOCKS_F32 3
+#endif
+template <typename T> __host__ __device__ constexpr int z_minblocks() { return sizeof(T) == 4 ? SCB_Z_MINBLOCKS_F32 : SCB_Z_MINBLOCKS; }
 __host__ __device__ constexpr int tz_for(int N) {
     return N >= 2048 ? 2 : N == 1024 ? 4 : N >= 256 ? SCB_ZTX_BIG : N == 128 ? 16 : 32;
 }
@@ -124,7 +131,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <typename T, int N, int KIND>
-__global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fused(const ZParams<T> p) {
+__global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fused(const ZParams<T> p) {
     using C = cx_t<T>;
     constexpr int TX = tz_for(N);
     constexpr int TPL = N / 8;
@@ -132,7 +139,13 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), SCB_Z_MINBLOCKS) k_z_fuse
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tx = threadIdx.x, j = threadIdx.y;
     const int kx = blockIdx.x * TX + tx;
-    const int kyl = blockIdx.y;        // line within this rank's ky slab
+    // Lines ky and Ly-ky read the same folded Green-spectrum rows: schedule them back to back so the
+    // second one finds them in L2 (single-GPU layout only; a rank's ky slab holds no such pairs).
+    int kyl = blockIdx.y;              // line within this rank's ky slab
+    if (p.ky0 == 0 && p.Ly == p.Lyg) {
+        const int b = blockIdx.y, m = b >> 1;
+        kyl = b == 0 ? 0 : b == 1 ? p.Ly / 2 : (b & 1) ? p.Ly - m : m;
+    }
     const int ky = p.ky0 + kyl;        // global ky: selects the Green-spectrum entries
     const bool valid = kx < p.ninner;
     LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
