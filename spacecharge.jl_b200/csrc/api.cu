@@ -77,6 +77,12 @@ struct scb_handle {
     int nranks = 1, rank = 0;
     void* slab = nullptr;          // reduce-scattered rho slab
     size_t slab_bytes = 0;
+    // peer-memory path: every rank maps the other ranks' arenas (CUDA IPC) and the pass kernels store
+    // straight into the destination rank's receive buffers
+    int p2p = -1;                  // -1 undecided, 0 off (NCCL send/recv), 1 on
+    unsigned long long arena_gen = 0, peer_gen = ~0ull;
+    std::vector<void*> peer_arena;
+    char* d_ipc = nullptr;         // nranks * 64 bytes of IPC handles + 2 ints (flag, barrier)
     cudaStream_t copy_stream = nullptr;
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -84,6 +90,8 @@ struct scb_handle {
 };
 
 namespace {
+
+void close_peers(scb_handle* h);  // defined with the multi-GPU code below
 
 int fail(scb_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
@@ -113,6 +121,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -135,6 +144,7 @@ bool load_nccl() {
     SCB_SYM(CommDestroy, "ncclCommDestroy")
     SCB_SYM(ReduceScatter, "ncclReduceScatter")
     SCB_SYM(AllGather, "ncclAllGather")
+    SCB_SYM(AllReduce, "ncclAllReduce")
     SCB_SYM(Send, "ncclSend")
     SCB_SYM(Recv, "ncclRecv")
     SCB_SYM(GroupStart, "ncclGroupStart")
@@ -183,6 +193,7 @@ int ensure_arena(scb_handle* h, size_t bytes) {
         return fail(h, SCB_ERR_ALLOC, "workspace allocation of " + std::to_string(bytes) + " bytes failed");
     }
     h->arena_bytes = bytes;
+    h->arena_gen++;
     return SCB_OK;
 }
 
@@ -686,6 +697,8 @@ int scb_destroy(scb_handle* h) {
     if (h->stage) cudaFree(h->stage);
     if (h->packed) cudaFree(h->packed);
     if (h->slab) cudaFree(h->slab);
+    close_peers(h);
+    if (h->d_ipc) cudaFree(h->d_ipc);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->d_bounds) cudaFree(h->d_bounds);
     if (h->ev_ready)
@@ -970,6 +983,72 @@ int64_t scb_workspace_bytes(const scb_handle* h) {
 // multi-GPU: NCCL is loaded lazily so that the library has no link-time dependency on it
 namespace {
 
+// Cross-rank barrier in stream order: a one-int all-reduce completes on a rank only after every rank
+// has reached it, i.e. after every rank's preceding kernels (and their peer stores) have finished.
+int rank_barrier(scb_handle* h) {
+    int* bar = reinterpret_cast<int*>(h->d_ipc + (size_t)SCB_MAX_RANKS * 64 + 4);
+    SCB_NCCL(h, g_nccl.AllReduce(bar, bar, 1, ncclInt32, ncclSum, h->comm, h->stream));
+    return SCB_OK;
+}
+
+void close_peers(scb_handle* h) {
+    for (int r = 0; r < (int)h->peer_arena.size(); ++r)
+        if (r != h->rank && h->peer_arena[r]) cudaIpcCloseMemHandle(h->peer_arena[r]);
+    h->peer_arena.clear();
+}
+
+// (Re)map the other ranks' arenas after this rank's arena was (re)allocated.  Collective: every rank
+// grows its arena in the same call, so every rank gets here together.  Any failure on any rank
+// switches all ranks back to the NCCL send/recv path.
+int exchange_arenas(scb_handle* h) {
+    if (h->p2p == 0 || (h->peer_gen == h->arena_gen && !h->peer_arena.empty())) return SCB_OK;
+    const int G = h->nranks, me = h->rank;
+    if (G > SCB_MAX_RANKS) { h->p2p = 0; return SCB_OK; }
+    if (h->p2p < 0) {
+        const char* e = std::getenv("SCB_P2P");
+        if (e && std::atoi(e) == 0) { h->p2p = 0; return SCB_OK; }
+    }
+    if (!h->d_ipc) {
+        SCB_CUDA(h, cudaMalloc(&h->d_ipc, (size_t)SCB_MAX_RANKS * 64 + 8));
+        SCB_CUDA(h, cudaMemsetAsync(h->d_ipc, 0, (size_t)SCB_MAX_RANKS * 64 + 8, h->stream));
+    }
+    close_peers(h);
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, h->arena) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof(mine)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SCB_CUDA(h, cudaMemcpyAsync(h->d_ipc + (size_t)me * 64, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+    SCB_NCCL(h, g_nccl.AllGather(h->d_ipc + (size_t)me * 64, h->d_ipc, 64, ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(G);
+    SCB_CUDA(h, cudaMemcpyAsync(all.data(), h->d_ipc, (size_t)G * 64, cudaMemcpyDeviceToHost, h->stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->peer_arena.assign(G, nullptr);
+    h->peer_arena[me] = h->arena;
+    for (int r = 0; r < G && ok; ++r) {
+        if (r == me) continue;
+        if (cudaIpcOpenMemHandle(&h->peer_arena[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            (void)cudaGetLastError();
+            h->peer_arena[r] = nullptr;
+            ok = 0;
+        }
+    }
+    // consensus: all ranks use the peer path or none does
+    int* flag = reinterpret_cast<int*>(h->d_ipc + (size_t)SCB_MAX_RANKS * 64);
+    SCB_CUDA(h, cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    SCB_NCCL(h, g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, h->comm, h->stream));
+    int all_ok = 0;
+    SCB_CUDA(h, cudaMemcpyAsync(&all_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!all_ok) {
+        close_peers(h);
+        h->p2p = 0;
+        return SCB_OK;
+    }
+    h->p2p = 1;
+    h->peer_gen = h->arena_gen;
+    return SCB_OK;
+}
+
 // all-to-all of equal contiguous blocks (block b of `send` goes to rank b; block g of `recv` comes
 // from rank g), `nsets` independent buffers (field components) in one NCCL group
 int all_to_all(scb_handle* h, const char* send, char* recv, size_t block_bytes, int nsets, size_t set_stride_bytes) {
@@ -1011,6 +1090,8 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
     const size_t szA = (size_t)pl.PX * pl.n[1] * nzl;       // A_l, D_c
     const size_t szB = (size_t)pl.PX * pl.L[1] * nzl;       // send/recv buffers (= PX*Lyl*nz)
     SCB_TRY(ensure_arena(h, (4 * szA + 8 * szB) * sizeof(C)));
+    SCB_TRY(exchange_arenas(h));
+    const bool p2p = h->p2p == 1;
     C* A = static_cast<C*>(h->arena);
     C* SB = A + szA;          // F2 output, blocked by destination rank
     C* RB = SB + szB;         // received: [z][ky_l][kx]
@@ -1039,10 +1120,16 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
         p.in_sline = pl.PX; p.in_souter = (long long)pl.PX * pl.n[1];
         p.out_sline = pl.PX; p.out_souter = (long long)pl.PX * Lyl;
         p.out_split = Lyl; p.out_sblock = (long long)blk;
+        if (p2p) {  // store block b straight into rank b's RB, at the slot reserved for this rank
+            p.use_peers = 1;
+            for (int r = 0; r < G; ++r)
+                p.out_peer[r] = static_cast<C*>(h->peer_arena[r]) + (RB - A) + (size_t)me * blk;
+        }
         p.scale = (T)1;
         SCB_CUDA(h, launch_lines<T>(pl.L[1], -1, p, nzl, 1, h->stream));
     }
-    SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(SB), reinterpret_cast<char*>(RB), blk * sizeof(C), 1, 0));
+    if (p2p) SCB_TRY(rank_barrier(h));
+    else SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(SB), reinterpret_cast<char*>(RB), blk * sizeof(C), 1, 0));
     tick(h, 10);
     {  // Z on this rank's ky slab
         ZParams<T> p{};
@@ -1052,10 +1139,17 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
         p.Ly = Lyl; p.Lyg = pl.L[1]; p.ky0 = me * Lyl;
         p.S = static_cast<const T*>(gfree->data); p.S_scomp = gfree->scomp;
         if (gaux) { p.H = static_cast<const C*>(gaux->data); p.H_scomp = gaux->scomp; }
+        if (p2p) {  // z planes of rank r go straight into rank r's R2, at the slot reserved for this rank
+            p.use_peers = 1;
+            p.out_split = nzl;
+            for (int r = 0; r < G; ++r)
+                p.out_peer[r] = static_cast<C*>(h->peer_arena[r]) + (R2 - A) + (size_t)me * blk;
+        }
         SCB_CUDA(h, launch_z_fused<T>(pl.L[2], mode == 0 ? GREEN_FREE : GREEN_CATHODE, p, h->stream));
     }
     tick(h, 11);
-    SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(Cc), reinterpret_cast<char*>(R2), blk * sizeof(C), 3, szB * sizeof(C)));
+    if (p2p) SCB_TRY(rank_barrier(h));
+    else SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(Cc), reinterpret_cast<char*>(R2), blk * sizeof(C), 3, szB * sizeof(C)));
     {  // B2, input blocked by source rank
         LinesParams<T> p{};
         p.in = R2; p.out = D; p.tw = twy;

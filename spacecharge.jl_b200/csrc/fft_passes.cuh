@@ -46,6 +46,10 @@ __host__ __device__ constexpr int tz_for(int N) {
 // line pairs per CTA in the x passes
 __host__ __device__ constexpr int lp_for(int N) { return (N / 8) >= 256 ? 1 : 256 / (N / 8); }
 
+#ifndef SCB_MAX_RANKS
+#define SCB_MAX_RANKS 16
+#endif
+
 enum GreenKind : int { GREEN_FREE = 0, GREEN_CATHODE = 1, GREEN_FULL = 2 };
 
 // ------------------------------------------------------------------------------------------
@@ -63,6 +67,10 @@ struct LinesParams {
     // peer rank; position pos lives at (pos % split)*sline + (pos / split)*sblock.  0 = contiguous.
     int in_split, out_split;
     long long in_sblock, out_sblock;
+    // peer-memory variant of the output split: block b is stored through out_peer[b] (a pointer into
+    // rank b's receive buffer, mapped over NVLink) -- the all-to-all is fused into the pass
+    int use_peers;
+    cx_t<T>* out_peer[SCB_MAX_RANKS];
     T scale;
 };
 
@@ -91,12 +99,16 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams
                                        : cmake<C>(0, 0);
     }
     fft_line<T, N, DIR>(v, lay, j, p.tw);
-    C* dst = p.out + (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
+    const long long dst_off = (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
-        if (valid && pos < p.n_out)
-            dst[line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = cscale(v[q], p.scale);
+        if (valid && pos < p.n_out) {
+            if (p.use_peers)
+                p.out_peer[pos / p.out_split][dst_off + (long long)(pos % p.out_split) * p.out_sline] = cscale(v[q], p.scale);
+            else
+                p.out[dst_off + line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = cscale(v[q], p.scale);
+        }
     }
 }
 
@@ -111,6 +123,10 @@ struct ZParams {
     int nz;                 // valid z planes in and out
     int ninner, PX, Ly;     // Ly: ky lines held by this rank (= plane pitch / PX)
     int Lyg, ky0;           // global padded y length and first global ky of this rank (Lyg = Ly, ky0 = 0 on one GPU)
+    // peer-memory output (multi-GPU): z plane pos goes to rank pos / out_split through out_peer[rank],
+    // at local plane pos % out_split -- the all-to-all back is fused into the pass
+    int use_peers, out_split;
+    cx_t<T>* out_peer[SCB_MAX_RANKS];
     // GREEN_FREE / GREEN_CATHODE: compressed real spectrum S_c[kx + PXg*(ky' + (Ly/2+1)*kz')],
     // Green_c = i * sign * S_c with ky' = min(ky, Ly-ky), kz' = min(kz, Lz-kz)
     const T* S;
@@ -221,11 +237,14 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
         }
         if (c < 2) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
         fft_line<T, N, +1>(w, lay, j, p.tw);
-        C* dst = p.out + c * p.out_scomp + (long long)kyl * p.PX + kx;
+        const long long dst_off = c * p.out_scomp + (long long)kyl * p.PX + kx;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int pos = j + q * TPL;
-            if (valid && pos < p.nz) dst[pos * plane] = w[q];
+            if (valid && pos < p.nz) {
+                if (p.use_peers) p.out_peer[pos / p.out_split][dst_off + (long long)(pos % p.out_split) * plane] = w[q];
+                else p.out[dst_off + pos * plane] = w[q];
+            }
         }
     }
 }
