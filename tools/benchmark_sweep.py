@@ -1,0 +1,78 @@
+"""Python twin of the reference's benchmark scripts (benchmark/deposit_benchmark.jl,
+solve_benchmark.jl, full_pipeline_benchmark.jl): the same six configurations, Float64, Gaussian bunch
+sigma = 1e-3 m, Q = 1e-9 C, seed 42; mesh construction and host->device copies outside the timed region;
+statistic = minimum over repetitions (@belapsed).  GPU = this library through the C ABI; CPU = the
+C restatement of the reference's structure (oracle/cpu_reference.py), timed on the host cores.
+
+usage: python tools/benchmark_sweep.py [--no-cpu] [--reps 10]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+CONFIGS = [((32,) * 3, 10_000), ((32,) * 3, 100_000), ((64,) * 3, 100_000), ((64,) * 3, 1_000_000),
+           ((128,) * 3, 100_000), ((128,) * 3, 1_000_000)]   # benchmark/full_pipeline_benchmark.jl:64-71
+
+
+def gpu_times(scb, grid, x, y, z, q, reps):
+    d = [torch.from_numpy(a).cuda() for a in (x, y, z, q)]
+    mesh = scb.Mesh3D(grid, *d[:3], total_charge=1e-9)
+    out = [torch.empty_like(d[0]) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    best = {"deposit": 1e9, "solve": 1e9, "interpolate": 1e9, "pipeline": 1e9}
+    for _ in range(reps + 2):
+        ev[0].record(); scb.deposit_(mesh, *d)
+        ev[1].record(); scb.solve_(mesh)
+        ev[2].record(); scb.interpolate_field(mesh, *d[:3])
+        ev[3].record(); torch.cuda.synchronize()
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); scb.step_(mesh, *d, *out); e1.record(); torch.cuda.synchronize()
+        for k, v in zip(("deposit", "solve", "interpolate"), t):
+            best[k] = min(best[k], v)
+        best["pipeline"] = min(best["pipeline"], e0.elapsed_time(e1))
+    return best, mesh
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    scb = load_package()
+    rows = []
+    print("%-8s %-9s | %9s %9s %9s %9s | %10s %8s" % ("grid", "particles", "dep ms", "solve ms", "interp ms", "pipe ms", "CPU pipe ms", "speedup"))
+    for grid, n in CONFIGS:
+        rng = np.random.default_rng(42)
+        x, y, z = (rng.standard_normal(n) * 1e-3 for _ in range(3))
+        q = np.full(n, 1e-9 / n)
+        g, mesh = gpu_times(scb, grid, x, y, z, q, args.reps)
+        cpu = None
+        if not args.no_cpu:
+            from oracle.cpu_reference import RefPort
+            rp = RefPort(grid, mesh.min_bounds, mesh.delta, 1.0)
+            best = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                rp.timed_step(x, y, z, q)
+                best = min(best, 1e3 * (time.perf_counter() - t0))
+            cpu = best
+        rows.append({"grid": grid[0], "particles": n, "gpu_ms": g, "cpu_pipeline_ms": cpu})
+        print("%-8s %-9d | %9.4f %9.4f %9.4f %9.4f | %10s %8s" % (
+            "%d^3" % grid[0], n, g["deposit"], g["solve"], g["interpolate"], g["pipeline"],
+            "%.1f" % cpu if cpu else "-", "%.0fx" % (cpu / g["pipeline"]) if cpu else "-"))
+    out = os.path.join(ROOT, "gpurun_out", "benchmark_sweep.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump({"cores": os.cpu_count(), "rows": rows}, open(out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
