@@ -302,22 +302,20 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         g.cnt[a] = g.sym[a] ? pl.n[a] + 1 : 2 * pl.n[a];
     }
     const size_t nP = (size_t)g.cnt[0] * g.cnt[1] * g.cnt[2];
-    const size_t nG = (size_t)pl.L[0] * pl.L[1] * pl.L[2];
     const size_t nS = (size_t)pl.PX * pl.L[1] * pl.L[2];
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     // free space: only ky <= Ly/2 and kz <= Lz/2 are kept, so the y pass prunes its output and the
     // z pass runs on half of the lines
     const int Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
     const bool prune = key.kind == 0;
-    const size_t nY2 = prune ? (size_t)pl.PX * Lyh1 * pl.L[2] : 0;
-    const size_t need = 2 * al(nP * 8) + al(nG * 8) + al(nS * 16) + al(nY2 * 16);
+    const size_t nY2 = nS;   // second full-size buffer: the passes ping-pong between the two
+    const size_t need = 2 * al(nP * 8) + al(nS * 16) + al(nY2 * 16);
     SCB_TRY(ensure_arena(h, need));
     char* base = static_cast<char*>(h->arena);
     double* P = reinterpret_cast<double*>(base);
     double* Dd = reinterpret_cast<double*>(base + al(nP * 8));
-    double* G = reinterpret_cast<double*>(base + 2 * al(nP * 8));
-    double2* spec = reinterpret_cast<double2*>(base + 2 * al(nP * 8) + al(nG * 8));
-    double2* Y2 = reinterpret_cast<double2*>(base + 2 * al(nP * 8) + al(nG * 8) + al(nS * 16));
+    double2* spec = reinterpret_cast<double2*>(base + 2 * al(nP * 8));
+    double2* Y2 = reinterpret_cast<double2*>(base + 2 * al(nP * 8) + al(nS * 16));
 
     const bool f64 = key.mdt == SCB_F64;
     size_t per_comp;  // elements
@@ -352,14 +350,30 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     SCB_TRY(get_twiddles<double>(h, pl.L[1], &twy));
     SCB_TRY(get_twiddles<double>(h, pl.L[2], &twz));
 
+    // Symmetric axes (zero offset, convolution placement): the padded IGF is even, or odd along the
+    // component's own axis, about index 0, so only rows Y <= Ly/2 (Z <= Lz/2) are transformed along x
+    // and the y (z) pass reads the missing half of each line mirrored with the parity sign.
+    const bool foldY = g.sym[1] && !g.corr[1];
+    const bool foldZ = g.sym[2] && !g.corr[2];
+    const int rowsY = foldY ? Lyh1 : pl.L[1];
+    const int rowsZ = foldZ ? Lzh1 : pl.L[2];
     for (int c = 0; c < 3; ++c) {
         SCB_CUDA(h, launch_green_point(P, g, c + 1, h->stream));
-        SCB_CUDA(h, launch_green_place(G, Dd, P, g, c + 1, sign_all, h->stream));
+        SCB_CUDA(h, launch_green_diff(Dd, P, g, h->stream));
         XParams<double> xp{};
-        xp.in = G;
-        xp.out = spec;
+        // the padded real array is generated inside the x pass (never written to memory)
+        xp.gen.D = Dd;
+        for (int a = 0; a < 3; ++a) {
+            xp.gen.n[a] = g.n[a]; xp.gen.L[a] = g.L[a]; xp.gen.sym[a] = g.sym[a]; xp.gen.corr[a] = g.corr[a];
+            xp.gen.dcnt[a] = g.cnt[a] - 1;
+        }
+        xp.gen.icomp = c + 1;
+        xp.gen.ly_lines = rowsY;
+        xp.gen.sign_all = sign_all;
+        xp.in = nullptr;
+        xp.out = spec;                                   // [kx][Y < rowsY][Z < rowsZ]
         xp.tw = twx;
-        xp.nlines = (long long)pl.L[1] * pl.L[2];
+        xp.nlines = (long long)rowsY * rowsZ;
         xp.real_sline = pl.L[0];
         xp.n_real = pl.L[0];
         xp.PX = pl.PX;
@@ -367,8 +381,8 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         SCB_CUDA(h, launch_x_r2c<double>(pl.L[0], xp, 1, h->stream));
         const int ly_out = prune ? Lyh1 : pl.L[1];   // ky kept after the y pass
         const int lz_out = prune ? Lzh1 : pl.L[2];
-        double2* ydst = prune ? Y2 : spec;
-        double2* zdst = spec;                        // pruned: [kx][ky<=Ly/2][kz<=Lz/2]; else in place
+        const bool y_in_place = !foldY && !prune;
+        double2* ydst = y_in_place ? spec : Y2;          // [kx][ky < ly_out][Z < rowsZ]
         LinesParams<double> yp{};
         yp.in = spec;
         yp.out = ydst;
@@ -377,10 +391,14 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         yp.n_out = ly_out;
         yp.ninner = pl.ninner;
         yp.in_sline = yp.out_sline = pl.PX;
-        yp.in_souter = (long long)pl.PX * pl.L[1];
+        yp.in_souter = (long long)pl.PX * rowsY;
         yp.out_souter = (long long)pl.PX * ly_out;
+        yp.in_fold = foldY ? 1 : 0;
+        yp.fold_sign = (c == 1) ? -1.0 : 1.0;
         yp.scale = 1.0;
-        SCB_CUDA(h, launch_lines<double>(pl.L[1], -1, yp, pl.L[2], 1, h->stream));
+        SCB_CUDA(h, launch_lines<double>(pl.L[1], -1, yp, rowsZ, 1, h->stream));
+        const bool z_in_place = y_in_place && !foldZ;    // same strides in and out
+        double2* zdst = z_in_place ? spec : (ydst == spec ? Y2 : spec);   // [kx][ky < ly_out][kz < lz_out]
         LinesParams<double> zp{};
         zp.in = ydst;
         zp.out = zdst;
@@ -390,13 +408,16 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         zp.ninner = pl.ninner;
         zp.in_sline = zp.out_sline = (long long)pl.PX * ly_out;
         zp.in_souter = zp.out_souter = pl.PX;
+        zp.in_fold = foldZ ? 1 : 0;
+        zp.fold_sign = (c == 2) ? -1.0 : 1.0;
         zp.scale = 1.0;
         SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, ly_out, 1, h->stream));
+        const double2* final_spec = zdst;
         char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
         if (key.kind == 0)
-            SCB_CUDA(h, launch_green_compress_free(dst, f64, spec, pl.ninner, pl.PX, Lyh1, Lzh1, h->stream));
+            SCB_CUDA(h, launch_green_compress_free(dst, f64, final_spec, pl.ninner, pl.PX, Lyh1, Lzh1, h->stream));
         else
-            SCB_CUDA(h, launch_green_convert_full(dst, f64, spec, pl.ninner, pl.PX, (long long)nS, h->stream));
+            SCB_CUDA(h, launch_green_convert_full(dst, f64, final_spec, pl.ninner, pl.PX, (long long)nS, h->stream));
         h->launches += 7;
     }
     return SCB_OK;

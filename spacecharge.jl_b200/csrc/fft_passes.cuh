@@ -71,6 +71,10 @@ struct LinesParams {
     // rank b's receive buffer, mapped over NVLink) -- the all-to-all is fused into the pass
     int use_peers;
     cx_t<T>* out_peer[SCB_MAX_RANKS];
+    // input known to be even (fold_sign = +1) or odd (-1) about index 0 (mod N): only positions
+    // 0..N/2 are stored, position pos > N/2 is read as fold_sign * in[N - pos]
+    int in_fold;
+    T fold_sign;
     T scale;
 };
 
@@ -95,8 +99,14 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
-        v[q] = (valid && pos < p.n_in) ? ld_stream(src + line_offset<T>(pos, p.in_sline, p.in_split, p.in_sblock))
-                                       : cmake<C>(0, 0);
+        if (p.in_fold) {
+            const bool hi = pos > N / 2;
+            const C t = valid ? __ldg(src + (long long)(hi ? N - pos : pos) * p.in_sline) : cmake<C>(0, 0);
+            v[q] = hi ? cscale(t, p.fold_sign) : t;
+        } else {
+            v[q] = (valid && pos < p.n_in) ? ld_stream(src + line_offset<T>(pos, p.in_sline, p.in_split, p.in_sblock))
+                                           : cmake<C>(0, 0);
+        }
     }
     fft_line<T, N, DIR>(v, lay, j, p.tw);
     const long long dst_off = (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
@@ -251,8 +261,41 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
 
 // ------------------------------------------------------------------------------------------
 // x passes: real <-> half-complex along the contiguous axis, two real lines per transform
+// Generator for the x pass of the Green-spectrum build: the padded, wrap-around-placed IGF array is
+// never materialised; element (X, Y, Z) is produced on the fly from the table D of differenced values
+// (one per distinct displacement).  Same mapping as k_green_place in green.cu.
+struct GreenGen {
+    const double* D;      // null: the pass reads real lines from memory
+    int n[3], L[3], sym[3], corr[3], dcnt[3];
+    int icomp;
+    int ly_lines;         // lines enumerate (Y, Z) with Y < ly_lines (L_y/2+1 when the y symmetry is exploited)
+    double sign_all;
+};
+
+// displacement bookkeeping of one axis: returns false when the index lies in the zero band
+__device__ __forceinline__ bool green_axis(const GreenGen& g, int a, int X, int& m0, double& sgn) {
+    const int n = g.n[a], L = g.L[a];
+    int d;
+    if (g.corr[a]) {
+        if (X > 2 * n - 2) return false;
+        d = X - (n - 1);
+    } else {
+        if (X <= n - 1) d = X;
+        else if (X >= L - (n - 1)) d = X - L;
+        else return false;
+    }
+    if (g.sym[a]) {
+        if (d < 0) { d = -d; if (a == g.icomp - 1) sgn = -sgn; }
+        m0 = d;
+    } else {
+        m0 = d + n - 1;
+    }
+    return true;
+}
+
 template <typename T>
 struct XParams {
+    GreenGen gen;
     const void* in;
     void* out;
     const cx_t<T>* tw;
@@ -264,7 +307,7 @@ struct XParams {
     T scale;
 };
 
-template <typename T, int N>
+template <typename T, int N, bool GEN>
 __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> p) {
     using C = cx_t<T>;
     constexpr int TPL = N / 8;
@@ -275,17 +318,39 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
     const long long la = 2 * pair, lb = 2 * pair + 1;
     const bool va = la < p.nlines, vb = lb < p.nlines;
     LayoutLine<C> lay(reinterpret_cast<C*>(smem_raw) + (size_t)lp * ROW);
-    const T* ra = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + la * p.real_sline;
-    const T* rb = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + lb * p.real_sline;
 
     C v[8];
+    if constexpr (GEN) {
+        // lines are (Y, Z) rows of the padded IGF array; resolve the y and z displacements once
+        const GreenGen& g = p.gen;
+        double sa = g.sign_all, sb = g.sign_all;
+        int ya = 0, za = 0, yb = 0, zb = 0;
+        bool oka = va, okb = vb;
+        if (oka) oka = green_axis(g, 1, (int)(la % g.ly_lines), ya, sa) && green_axis(g, 2, (int)(la / g.ly_lines), za, sa);
+        if (okb) okb = green_axis(g, 1, (int)(lb % g.ly_lines), yb, sb) && green_axis(g, 2, (int)(lb / g.ly_lines), zb, sb);
+        const long long rowa = (long long)g.dcnt[0] * (ya + (long long)g.dcnt[1] * za);
+        const long long rowb = (long long)g.dcnt[0] * (yb + (long long)g.dcnt[1] * zb);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int pos = j + q * TPL;
-        const bool in_range = pos < p.n_real;
-        const T a = (va && in_range) ? ld_stream(ra + pos) : (T)0;
-        const T b = (vb && in_range) ? ld_stream(rb + pos) : (T)0;
-        v[q] = cmake<C>(a, b);
+        for (int q = 0; q < 8; ++q) {
+            const int pos = j + q * TPL;
+            int mx = 0;
+            double sx = 1.0;
+            const bool okx = green_axis(g, 0, pos, mx, sx);
+            const double a = (oka && okx) ? sa * sx * __ldg(g.D + rowa + mx) : 0.0;
+            const double b = (okb && okx) ? sb * sx * __ldg(g.D + rowb + mx) : 0.0;
+            v[q] = cmake<C>((T)a, (T)b);
+        }
+    } else {
+        const T* ra = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + la * p.real_sline;
+        const T* rb = static_cast<const T*>(p.in) + (long long)blockIdx.y * p.real_scomp + lb * p.real_sline;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int pos = j + q * TPL;
+            const bool in_range = pos < p.n_real;
+            const T a = (va && in_range) ? ld_stream(ra + pos) : (T)0;
+            const T b = (vb && in_range) ? ld_stream(rb + pos) : (T)0;
+            v[q] = cmake<C>(a, b);
+        }
     }
     fft_line<T, N, -1>(v, lay, j, p.tw);
 

@@ -6,9 +6,9 @@
 // The reference fills the whole doubled (2n)^3 array point-wise and differences it, three times
 // per solve.  Here the point-wise values are produced only on the corner ranges that are needed
 // (an octant when the offset along an axis is zero: the IGF is odd along its own axis and even
-// along the other two), the 8-point differencing is fused into the kernel that places the IGF
-// into the zero-padded, wrap-around array handed to the FFT passes, and the resulting spectrum is
-// cached per geometry by the caller (api.cu).
+// along the other two), differenced once per distinct displacement, and the zero-padded wrap-around
+// array the FFT needs is generated inside the first FFT pass instead of being written to memory;
+// the resulting spectrum is cached per geometry by the caller (api.cu).
 //
 // Compiled with -fmad=false so that u = (i-1)*dx + umin and the closed form round exactly like
 // the reference's un-contracted Julia arithmetic.
@@ -78,43 +78,10 @@ __global__ void k_green_diff(double* __restrict__ D, const double* __restrict__ 
     D[idx] = diff8(P, g.cnt[0], g.cnt[1], a, b, c);
 }
 
-// Placement of the differenced values into the padded real array g[X + Lx*(Y + Ly*Z)].
-// axis modes: conv = wrap-around placement of displacement d at index d mod L;
-//             corr = displacement d at index d + (n-1) (image charge along z).
-// Symmetric axes read |d| and flip the sign when the axis is the component's own (odd) axis.
-__global__ void k_green_place(double* __restrict__ gout, const double* __restrict__ D, IgfGeom g, int icomp, double sign_all) {
-    const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    int X[3];
-    X[0] = (int)(idx % g.L[0]);
-    X[1] = (int)((idx / g.L[0]) % g.L[1]);
-    X[2] = (int)(idx / ((long long)g.L[0] * g.L[1]));
-    int m0[3];
-    double sgn = sign_all;
-    bool zero = false;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int n = g.n[a], L = g.L[a];
-        int d;
-        if (g.corr[a]) {
-            if (X[a] <= 2 * n - 2) d = X[a] - (n - 1);
-            else { zero = true; d = 0; }
-        } else {
-            if (X[a] <= n - 1) d = X[a];
-            else if (X[a] >= L - (n - 1)) d = X[a] - L;
-            else { zero = true; d = 0; }
-        }
-        if (g.sym[a]) {           // octant stored: corners i0 = n (1-based) .. 2n
-            if (d < 0) { d = -d; if (a == icomp - 1) sgn = -sgn; }
-            m0[a] = d;
-        } else {                  // full range stored: corners 1 .. 2n
-            m0[a] = d + n - 1;
-        }
-    }
-    const int dcx = g.cnt[0] - 1, dcy = g.cnt[1] - 1;
-    gout[idx] = zero ? 0.0 : sgn * __ldg(D + m0[0] + (long long)dcx * (m0[1] + (long long)dcy * m0[2]));
-}
+// The placement of the differenced values into the padded, wrap-around real array (displacement d at
+// index d mod L, or d + n-1 along a correlation axis; symmetric axes read |d| with the parity sign)
+// happens on the fly inside the x pass of the spectrum build: see GreenGen / green_axis in
+// fft_passes.cuh.
 
 // Spectrum -> cached forms.
 // free space: Green_c = i*S_c, S_c real; the passes already pruned the spectrum to kx<=Lx/2,
@@ -152,11 +119,9 @@ cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P
     return cudaGetLastError();
 }
 
-cudaError_t launch_green_place(double* gout, double* D, const double* P, const IgfGeom& g, int icomp, double sign_all, cudaStream_t s) {
+cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cudaStream_t s) {
     const long long nd = (long long)(g.cnt[0] - 1) * (g.cnt[1] - 1) * (g.cnt[2] - 1);
     k_green_diff<<<blocks_for(nd, 256), 256, 0, s>>>(D, P, g);
-    const long long total = (long long)g.L[0] * g.L[1] * g.L[2];
-    k_green_place<<<blocks_for(total, 256), 256, 0, s>>>(gout, D, g, icomp, sign_all);
     return cudaGetLastError();
 }
 

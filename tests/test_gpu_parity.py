@@ -145,11 +145,13 @@ def test_solve_matches_oracle_f32(scb, oracle, record, at_cathode):
         check(record, "E%d" % c, got[..., c], ref.efield[..., c], TOL32)
 
 
-def test_solve_freespace_general_offset(scb, oracle, record):
+@pytest.mark.parametrize("off", [(0.3e-3, -0.2e-3, 1.7e-3), (0.0, 0.0, 1.7e-3), (0.3e-3, 0.0, 0.0), (0.0, -0.2e-3, 0.0)])
+def test_solve_freespace_general_offset(scb, oracle, record, off):
+    """solve_freespace!(mesh; offset) with symmetry broken along all / one axis (the spectrum build
+    exploits the remaining symmetric axes)."""
     grid = (6, 10, 5)
     rng = np.random.default_rng(3)
     rho = rng.standard_normal(grid)
-    off = (0.3e-3, -0.2e-3, 1.7e-3)
     ref = oracle.mesh_from_bounds(grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), gamma=1.5)
     mesh = scb.Mesh3D(grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), gamma=1.5)
     ref.rho[...] = rho
