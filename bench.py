@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stages-only", action="store_true", help="print only the per-stage device times (tuning)")
     ap.add_argument("--replicated-solve", action="store_true", help="multi-GPU: all-reduce rho and solve on every rank")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-structure-on-GPU baseline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +354,31 @@ def main():
                "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * float(tt.item()), "steps": ksteps,
                "api": "pinned host shards -> step_ -> pinned host outputs, per rank"}
 
+    # secondary baseline: the reference's GPU structure (1 thread/particle atomics, 7 in-place Z2Z cuFFTs and
+    # ~20 element-wise launches per solve, 24-gather interpolation) restated in plain CUDA, on the same GPU
+    gpu_ref = None
+    if rank == 0 and world == 1 and s == 8 and not args.no_gpu_baseline:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("naive_gpu_driver", os.path.join(ROOT, "baseline", "naive_gpu", "driver.py"))
+            drv = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(drv)
+            rg = drv.RefGpu()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            best = None
+            for _ in range(4):
+                rg.step(grid, mesh.min_bounds, mesh.max_bounds, mesh.delta, 1.0, at_cathode, x, y, z, q, mesh._rho, mesh._efield,
+                        ex, ey, ez, events=ev)
+                torch.cuda.synchronize()
+                cur = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+                best = cur if best is None else [min(a, b) for a, b in zip(best, cur)]
+            gpu_ref = {"what": "reference structure restated in plain CUDA + cuFFT Z2Z (baseline/naive_gpu), same B200",
+                       "ms_per_step": sum(best), "value": npart / (sum(best) * 1e-3), "unit": "particles/s",
+                       "stages_ms": {"deposit": best[0], "solve": best[1], "interpolate": best[2]}}
+            del rg
+        except Exception as exc:   # the baseline is optional evidence, never a reason to lose the bench line
+            gpu_ref = {"unavailable": repr(exc)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del x, y, z, q, ex, ey, ez
@@ -368,6 +394,7 @@ def main():
             "dtype": args.dtype, "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(), "roofline": roofline, "stage_roofline": stage_roof,
             "solve_ms": stage["solve"], "cold_geometry": cold, "cpu_baseline": cpu_baseline,
+            "gpu_reference_structure": gpu_ref,
             "workspace_GB": hd.workspace_bytes() / 1e9,
         }
         print(json.dumps(line))
