@@ -56,7 +56,7 @@ typedef enum scb_status {
 typedef struct scb_options {
     int32_t green_cache;       /* 1 (default): keep the IGF spectrum per geometry; 0: rebuild every
                                   solve like the reference does (src/solvers/free_space.jl:79-89) */
-    int32_t deposit_mode;      /* 0 = auto, 1 = one thread per particle with global reductions     */
+    int32_t deposit_mode;      /* 0 = auto, 1 = one thread per particle, 2 = lane pairs, 3 = cell tiles  */
     int32_t reserved[6];
 } scb_options;
 

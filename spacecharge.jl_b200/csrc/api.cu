@@ -64,6 +64,8 @@ struct scb_handle {
     unsigned long long* d_bounds = nullptr;
     void* packed = nullptr;       // node-major copy of efield for the gather (32 bytes per node)
     size_t packed_bytes = 0;
+    void* tiles = nullptr;        // cell-tile accumulator of the deposit (4 mesh elements per node)
+    size_t tiles_bytes = 0;
     int64_t launches = 0;
     // timing
     bool timing = false;
@@ -233,6 +235,33 @@ int ensure_packed(scb_handle* h, size_t bytes) {
         return fail(h, SCB_ERR_ALLOC, "packed-field allocation failed");
     }
     h->packed_bytes = bytes;
+    return SCB_OK;
+}
+
+// deposit: cell-tile accumulation when there are enough particles to pay for zeroing and folding the
+// tiles (deposit_mode 0 = auto, 1 = one thread per particle, 2 = lane pairs, 3 = tiles)
+int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
+                void* rho, int mdt, const Geom3& g, bool clear, bool cleared_already) {
+    const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
+    int mode = h->opt.deposit_mode;
+    if (mode == 0) mode = np >= ng ? 3 : 2;
+    if (mode == 3) {
+        const size_t need = (size_t)4 * ng * dt_size(mdt);
+        if (h->tiles_bytes < need) {
+            if (h->tiles) { SCB_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(h->tiles); h->tiles = nullptr; h->tiles_bytes = 0; }
+            if (cudaMalloc(&h->tiles, need) != cudaSuccess) { (void)cudaGetLastError(); mode = 2; }
+            else h->tiles_bytes = need;
+        }
+    }
+    if (mode == 3) {
+        // a cleared rho equals "overwrite"; an un-cleared one is accumulated into
+        SCB_CUDA(h, launch_deposit_tiles(pdt, mdt, np, x, y, z, q, h->tiles, rho, g, clear ? 0 : 1, h->stream));
+        h->launches += 2;
+        return SCB_OK;
+    }
+    if (clear && !cleared_already) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)ng * dt_size(mdt), h->stream));
+    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, g, mode, h->stream));
+    if (np > 0) h->launches += 1;
     return SCB_OK;
 }
 
@@ -717,6 +746,7 @@ int scb_destroy(scb_handle* h) {
     if (h->arena) cudaFree(h->arena);
     if (h->stage) cudaFree(h->stage);
     if (h->packed) cudaFree(h->packed);
+    if (h->tiles) cudaFree(h->tiles);
     if (h->slab) cudaFree(h->slab);
     close_peers(h);
     if (h->d_ipc) cudaFree(h->d_ipc);
@@ -795,11 +825,9 @@ int scb_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const v
     SCB_TRY(check_grid(h, n));
     SCB_CUDA(h, cudaSetDevice(h->device));
     tick(h, 0);
-    if (clear) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
-    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, make_geom(n, min_bounds, delta), h->opt.deposit_mode, h->stream));
+    SCB_TRY(run_deposit(h, np, x, y, z, q, pdt, rho, mdt, make_geom(n, min_bounds, delta), clear != 0, false));
     tick(h, 1);
     h->t_dep = true;
-    if (np > 0) h->launches += 1;
     return SCB_OK;
 }
 
@@ -992,7 +1020,7 @@ int scb_drop_green_cache(scb_handle* h) {
 
 int64_t scb_workspace_bytes(const scb_handle* h) {
     if (!h) return 0;
-    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes;
+    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes + (int64_t)h->tiles_bytes;
     for (auto& e : h->green) b += (int64_t)e.cap;
     for (auto& e : h->green_pool) b += (int64_t)e.second;
     return b;

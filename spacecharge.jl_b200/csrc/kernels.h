@@ -35,6 +35,10 @@ cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, 
 // mode 1: one thread per particle; otherwise two lanes per particle (x-neighbours coalesce in L2)
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                            const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s);
+// cell-tile deposit: `tiles` = 4 * Ng mesh elements of scratch; zeroes it, accumulates, folds into rho
+// (rho is overwritten, or added to when accumulate != 0)
+cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
 // node-major repack of efield (32 bytes per node) and the gather that reads it

@@ -118,6 +118,69 @@ __global__ void __launch_bounds__(256) k_deposit_pair(long long np, const P* __r
     }
 }
 
+// ---- deposit, cell-tile variant ---------------------------------------------------------------
+// The L2 reduction path charges per 32-byte sector transaction, not per value (k_deposit: 8 per
+// particle, 4.1 ms; k_deposit_pair: 5 per particle, 2.65 ms at 1e8 particles / 256^3 Float64).  Here
+// the particle does not update the grid nodes but a private accumulator laid out per CELL: tile
+// (ix,iy,iz) = the four (x,y) corner values of cell (ix,iy) in plane iz, 4 values = one 32-byte
+// sector in Float64.  Four adjacent lanes share a particle (lane&3 = x corner + 2*y corner) and issue
+// two reduction instructions (plane iz, plane iz+1): 2 sector transactions per particle.  A second
+// kernel folds the tiles into rho: node (i,j,k) = T(i,j,k)[0] + T(i-1,j,k)[1] + T(i,j-1,k)[2] +
+// T(i-1,j-1,k)[3] (fixed order).  Per-contribution values are the reference's ((q*wx)*wy)*wz.
+template <typename P, typename T>
+__global__ void __launch_bounds__(256) k_deposit_tiles(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                        const P* __restrict__ z, const P* __restrict__ q,
+                                                        T* __restrict__ tiles, const Geom3 g) {
+    using W = typename promote<P, T>::type;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const int k = lane & 3, kx = k & 1, ky = k >> 1;
+    for (long long base = warp * 32; base < np; base += nwarps * 32) {
+        const long long i = base + lane;
+        W f0 = 0, f1 = 0, f2 = 0, charge = 0;
+        long long off = 0;
+        if (i < np) {
+            CellW<W> c;
+            locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+            charge = (W)ld_stream(q + i);
+            f0 = c.f[0]; f1 = c.f[1]; f2 = c.f[2];
+            off = c.i[0] + sy * c.i[1] + sz * c.i[2];
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int src = 8 * h + (lane >> 2);
+            const W fx = __shfl_sync(FULL, f0, src);
+            const W fy = __shfl_sync(FULL, f1, src);
+            const W fz = __shfl_sync(FULL, f2, src);
+            const W qq = __shfl_sync(FULL, charge, src);
+            const long long o = __shfl_sync(FULL, off, src);
+            if (base + src < np) {
+                const W one = (W)1;
+                const W qxy = qq * (kx ? fx : one - fx) * (ky ? fy : one - fy);   // (charge * w_x) * w_y
+                T* t = tiles + 4 * o + k;
+                atomicAdd(t, (T)(qxy * (one - fz)));
+                atomicAdd(t + 4 * sz, (T)(qxy * fz));
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fold_tiles(const T* __restrict__ tiles, T* __restrict__ rho, int nx, int ny,
+                                                     long long ng, int accumulate) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ng) return;
+    const int i = (int)(idx % nx), j = (int)((idx / nx) % ny);
+    T s = __ldg(tiles + 4 * idx);
+    if (i > 0) s += __ldg(tiles + 4 * (idx - 1) + 1);
+    if (j > 0) s += __ldg(tiles + 4 * (idx - nx) + 2);
+    if (i > 0 && j > 0) s += __ldg(tiles + 4 * (idx - nx - 1) + 3);
+    rho[idx] = accumulate ? rho[idx] + s : s;
+}
+
 // ---- interpolate: one thread per particle, 24 gathers --------------------------------------
 template <typename P, typename T>
 __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __restrict__ x, const P* __restrict__ y,
@@ -430,6 +493,23 @@ cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, co
 #define CALL(P, T) k_interpolate<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez);
     SCB_DISPATCH_PT(CALL)
 #undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s) {
+    const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
+    cudaError_t e = cudaMemsetAsync(tiles, 0, (size_t)4 * ng * (mdt == 1 ? 8 : 4), s);
+    if (e != cudaSuccess) return e;
+    if (np > 0) {
+        const unsigned grid = particle_grid(np, 256, 64);
+#define CALL(P, T) k_deposit_tiles<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)tiles, g);
+        SCB_DISPATCH_PT(CALL)
+#undef CALL
+    }
+    const unsigned fgrid = (unsigned)((ng + 255) / 256);
+    if (mdt == 1) k_fold_tiles<double><<<fgrid, 256, 0, s>>>((const double*)tiles, (double*)rho, g.n[0], g.n[1], ng, accumulate);
+    else k_fold_tiles<float><<<fgrid, 256, 0, s>>>((const float*)tiles, (float*)rho, g.n[0], g.n[1], ng, accumulate);
     return cudaGetLastError();
 }
 
