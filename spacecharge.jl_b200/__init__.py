@@ -308,6 +308,16 @@ class Mesh3D:
                 % (np.dtype(self.T).name, nx, ny, nz, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], self.gamma))
 
     # helpers for the ABI calls
+    def remesh_(self, particles_x, particles_y, particles_z):
+        """Re-fit the bounds and spacing to new particle positions in place (what a tracking loop does
+        every step by calling the particle-based constructor again, src/mesh.jl:95-174) without
+        re-allocating rho / efield.  The extrema come from one fused device reduction (scb_bounds); the
+        next solve_ rebuilds the Green spectrum for the new spacing (cold-geometry path)."""
+        npdt = np.dtype(self.T).type
+        self.min_bounds, self.max_bounds, self.delta = self._auto_bounds(
+            self.grid_size, particles_x, particles_y, particles_z, npdt, self.device, self.handle, self.group)
+        return self
+
     def reduce_rho_(self):
         """Sum the per-rank partial charge grids in place (sharded mode keeps them partial)."""
         if self.group is not None:
