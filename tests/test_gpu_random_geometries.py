@@ -48,3 +48,26 @@ def test_random_geometry_solve_and_step(scb, oracle, record, seed):
     wscale = max(np.abs(w).max() for w in want)
     for c in range(3):
         assert float(np.abs(got[c].cpu().numpy() - want[c]).max() / wscale) < tol
+
+
+@pytest.mark.parametrize("grid", [(1024, 2, 3), (2, 1024, 2), (3, 2, 1024), (512, 4, 2), (2, 2, 2), (129, 3, 65)])
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_extreme_aspect_ratios(scb, oracle, record, grid, at_cathode):
+    """Largest supported axis (n = 1024, padded transform length 2048), the smallest grid (2,2,2) and
+    sizes just above a power of two (129 -> padded 512)."""
+    import torch
+    rng = np.random.default_rng(sum(grid))
+    rho = rng.standard_normal(grid)
+    lo, hi = (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3)
+    ref = oracle.mesh_from_bounds(grid, lo, hi, gamma=2.0)
+    ref.rho[...] = rho
+    oracle.solve(ref, at_cathode=at_cathode)
+    mesh = scb.Mesh3D(grid, lo, hi, gamma=2.0)
+    mesh.rho.copy_(torch.from_numpy(rho).cuda())
+    scb.solve_(mesh, at_cathode=at_cathode)
+    e = mesh.efield.cpu().numpy()
+    scale = max(np.abs(ref.efield[..., c]).max() for c in range(3))
+    for c in range(3):
+        err = float(np.abs(e[..., c] - ref.efield[..., c]).max() / scale)
+        record("E%d grid=%s cath=%s" % (c, grid, at_cathode), err, 1e-10)
+        assert err < 1e-10
