@@ -56,7 +56,7 @@ def algorithmic_bytes(npart, grid, s, at_cathode):
     A = kx * ny * nz * 2 * s
     B = kx * L[1] * nz * 2 * s
     G = 3 * kx * (L[1] // 2 + 1) * (L[2] // 2 + 1) * s
-    Gimg = 3 * kx * L[1] * L[2] * 2 * s if at_cathode else 0
+    Gimg = 3 * kx * (L[1] // 2 + 1) * L[2] * 2 * s if at_cathode else 0   # image spectrum, ky folded
     return {
         "deposit": 4 * npart * s + ng * s,
         "interpolate": 6 * npart * s + 3 * ng * s,

@@ -333,10 +333,12 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     const size_t nP = (size_t)g.cnt[0] * g.cnt[1] * g.cnt[2];
     const size_t nS = (size_t)pl.PX * pl.L[1] * pl.L[2];
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    // free space: only ky <= Ly/2 and kz <= Lz/2 are kept, so the y pass prunes its output and the
-    // z pass runs on half of the lines
+    // free space and image charge: only ky <= Ly/2 and kz <= Lz/2 are kept (the y pass prunes its output,
+    // the z pass runs on half of the lines and prunes too).  Free space: the spectrum is i*S with S real and
+    // (anti)symmetric.  Image charge: h is real, even/odd in x and y with parities p_x, p_y, general in z, so
+    // H(kx, Ly-ky, kz) = p_y H(kx,ky,kz) and H(kx, ky, Lz-kz) = p_x p_y conj(H(kx,ky,kz)).
     const int Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
-    const bool prune = key.kind == 0;
+    const bool prune = key.kind == 0 || key.kind == 1;
     const size_t nY2 = nS;   // second full-size buffer: the passes ping-pong between the two
     const size_t need = 2 * al(nP * 8) + al(nS * 16) + al(nY2 * 16);
     SCB_TRY(ensure_arena(h, need));
@@ -348,7 +350,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
 
     const bool f64 = key.mdt == SCB_F64;
     size_t per_comp;  // elements
-    if (key.kind == 0) per_comp = (size_t)pl.PX * Lyh1 * Lzh1;
+    if (prune) per_comp = (size_t)pl.PX * Lyh1 * Lzh1;
     else per_comp = nS;
     const size_t elem = (key.kind == 0 ? 1 : 2) * dt_size(key.mdt);
     ent.bytes = 3 * per_comp * elem;
@@ -446,7 +448,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         if (key.kind == 0)
             SCB_CUDA(h, launch_green_compress_free(dst, f64, final_spec, pl.ninner, pl.PX, Lyh1, Lzh1, h->stream));
         else
-            SCB_CUDA(h, launch_green_convert_full(dst, f64, final_spec, pl.ninner, pl.PX, (long long)nS, h->stream));
+            SCB_CUDA(h, launch_green_convert_full(dst, f64, final_spec, pl.ninner, pl.PX, (long long)per_comp, h->stream));
         h->launches += 7;
     }
     return SCB_OK;

@@ -141,7 +141,9 @@ struct ZParams {
     // Green_c = i * sign * S_c with ky' = min(ky, Ly-ky), kz' = min(kz, Lz-kz)
     const T* S;
     long long S_scomp;
-    // GREEN_CATHODE: image spectrum H_c, GREEN_FULL: G_c; complex [kx + PX*(ky + Ly*kz)]
+    // GREEN_CATHODE: image spectrum H_c, complex, folded like S: [kx + PX*(ky' + (Ly/2+1)*kz')] with
+    //   H(ky > Ly/2) = p_y H(Ly-ky), H(kz > Lz/2) = p_x p_y conj(H(Lz-kz)), p = -1 along the component's axis
+    // GREEN_FULL: G_c, complex, unfolded [kx + PX*(ky + Ly*kz)]
     const cx_t<T>* H;
     long long H_scomp;
 };
@@ -234,7 +236,11 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
                     acc = cmake<C>(-spec[q].y * s, spec[q].x * s);
                 }
                 if constexpr (KIND == GREEN_CATHODE) {
-                    const C h = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Lyg * kz));
+                    const int kzf = kz <= N / 2 ? kz : N - kz;
+                    C h = __ldg(p.H + c * p.H_scomp + kx + (long long)p.PX * (kyf + (long long)(Lyh + 1) * kzf));
+                    const T py = (c == 1) ? (T)-1 : (T)1, pxy = (c == 0 || c == 1) ? (T)-1 : (T)1;
+                    if (ky > Lyh) h = cscale(h, py);
+                    if (kz > N / 2) h = cmake<C>(pxy * h.x, -pxy * h.y);
                     const C m = laym.ld((N - kz) & (N - 1));
                     acc = cadd(acc, cmul(m, h));
                 }
