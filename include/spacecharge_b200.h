@@ -98,18 +98,46 @@ SCB_API int scb_solve_freespace(scb_handle* h, const void* rho, void* efield, in
                         const int64_t n[3], const double delta[3], double gamma,
                         const double offset[3]);
 
+/* ---- extension: scalar potential and magnetic field ---------------------- */
+/* The reference stores only rho and efield (src/mesh.jl:19-34); its potential_green_function
+ * (src/green_functions.jl:13-22) is defined but unreachable because get_green_kernel! returns zero for
+ * icomp outside 1..3 (src/green_functions.jl:90-98).  scb_solve_potential runs the same convolution
+ * with that function as a fourth component (icomp = 0 with factor 1/(dx*dy*dz), the convention of the
+ * upstream OpenSpaceCharge code the reference README cites) and writes phi (nx,ny,nz) next to efield:
+ *     phi[p] = FPEI * sum_n rho[n] * IGF_phi((p - n) * delta [+ image term when at_cathode])
+ * i.e. the potential in the bunch rest frame (dz = delta_z * gamma), so that E_{x,y} = -gamma * d(phi)/d{x,y}
+ * and E_z = -(1/gamma) * d(phi)/dz on the lab-frame mesh.  efield is written exactly as by scb_solve. */
+SCB_API int scb_solve_potential(scb_handle* h, const void* rho, void* efield, void* phi, int mdt,
+                                const int64_t n[3], const double min_bounds[3], const double max_bounds[3],
+                                const double delta[3], double gamma, int at_cathode);
+/* Magnetic field of a bunch moving along +z with the mesh's gamma: B = (beta/c) z_hat x E, i.e.
+ * Bx = -(beta/c) Ey, By = (beta/c) Ex, Bz = 0; bfield has the layout of efield. */
+SCB_API int scb_bfield(scb_handle* h, const void* efield, void* bfield, int mdt, const int64_t n[3],
+                       double gamma);
+
 /* ---- a14: interpolate_field  (src/interpolation.jl:17-128) -------------------------------- */
 SCB_API int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
                     int pdt, const void* efield, int mdt, const int64_t n[3],
                     const double min_bounds[3], const double delta[3],
                     void* ex, void* ey, void* ez);
 
+/* ---- extension: interpolation fused with the momentum kick ---------------- */
+/* Same gather as scb_interpolate, but instead of returning E it updates the caller's momentum
+ * arrays in place: px += coef_xy*Ex, py += coef_xy*Ey, pz += coef_z*Ez (product and sum formed
+ * separately in promote(pdt, mdt), rounded to pdt once) -- E never round-trips through memory.
+ * For a bunch moving along z the Lorentz force q(E + v x B) gives coef_xy = q*dt/gamma^2, coef_z = q*dt. */
+SCB_API int scb_interpolate_kick(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                                 int pdt, const void* efield, int mdt, const int64_t n[3],
+                                 const double min_bounds[3], const double delta[3],
+                                 void* px, void* py, void* pz, double coef_xy, double coef_z);
+
 /* ---- a8-a11: get_green_function!  (src/green_functions.jl:41-112), parity hook ----------- */
 /* Writes the integrated Green function in the reference's layout: a REAL array of shape
  * n2 = (2nx, 2ny, 2nz) (the real part of the reference's complex cgrn; its imaginary part is
  * zero), entry (i,j,k) for displacement (i+1-nx, j+1-ny, k+1-nz); the last plane of every
  * dimension holds the raw point-wise values exactly like the reference leaves them.
- * Always evaluated in double; `dt` selects the output element type. */
+ * Always evaluated in double; `dt` selects the output element type.  icomp = 1,2,3 as in the
+ * reference; icomp = 0 gives the potential Green function used by scb_solve_potential. */
 SCB_API int scb_green(scb_handle* h, void* cgrn_real_out, const int64_t n2[3], const double delta[3],
               double gamma, int icomp, const double offset[3], int dt);
 

@@ -63,6 +63,7 @@ class Mesh3D:
     efield: np.ndarray
     T: type = np.float64
     _workspace: Optional[dict] = field(default=None, repr=False)
+    phi: Optional[np.ndarray] = field(default=None, repr=False)   # extension, see solve(..., potential=True)
 
 
 def _alloc(grid_size, T):
@@ -217,7 +218,7 @@ def field_green_function(x, y, z):
     return x * np.arctan((y * z) / (r * x)) - z * np.log(r + y) + y * np.log((r - z) / (r + z)) / 2
 
 
-def green_pointwise(shape2, delta, gamma, icomp, offset=(0.0, 0.0, 0.0), T=np.float64):
+def green_pointwise(shape2, delta, gamma, icomp, offset=(0.0, 0.0, 0.0), T=np.float64, potential_icomp0=False):
     """get_green_kernel!, src/green_functions.jl:69-101 (real part; imaginary part is zero)."""
     T = np.dtype(T).type
     isize, jsize, ksize = shape2
@@ -241,6 +242,10 @@ def green_pointwise(shape2, delta, gamma, icomp, offset=(0.0, 0.0, 0.0), T=np.fl
             g = field_green_function(v, w, u) * factor
         elif icomp == 3:
             g = field_green_function(w, u, v) * factor
+        elif icomp == 0 and potential_icomp0:
+            # EXTENSION (not reachable in the reference, whose kernel returns zero here): the potential
+            # Green function with the factor 1/(dx*dy*dz) of the `else` branch of :77-81
+            g = potential_green_function(u, v, w) * factor
         else:
             g = np.zeros((isize, jsize, ksize), dtype=T)
     return np.asfortranarray(g.astype(T))
@@ -252,13 +257,13 @@ def difference_8point(c):
             - c[:-1, :-1, :-1] + c[:-1, :-1, 1:] + c[:-1, 1:, :-1] + c[1:, :-1, :-1])
 
 
-def get_green_function(shape2, delta, gamma, icomp, offset=(0.0, 0.0, 0.0), T=np.float64):
+def get_green_function(shape2, delta, gamma, icomp, offset=(0.0, 0.0, 0.0), T=np.float64, potential_icomp0=False):
     """get_green_function!, src/green_functions.jl:41-67.
 
     Point-wise fill, 8-point differencing into the leading (2n-1)^3 block; the last
     plane of every dimension keeps its raw point-wise values (:64-66).
     """
-    g = green_pointwise(shape2, delta, gamma, icomp, offset, T)
+    g = green_pointwise(shape2, delta, gamma, icomp, offset, T, potential_icomp0)
     out = g.copy(order="F")
     out[:-1, :-1, :-1] = difference_8point(g)
     return out
@@ -270,9 +275,12 @@ def _fftn(a, inverse=False):
     return f(a, workers=_workers())
 
 
-def solve_freespace(mesh: Mesh3D, offset=(0.0, 0.0, 0.0)) -> None:
+def solve_freespace(mesh: Mesh3D, offset=(0.0, 0.0, 0.0), potential: bool = False) -> None:
     """solve_freespace!, src/solvers/free_space.jl:56-101 (same structure: padded C2C
-    FFT of rho, then per component IGF -> FFT -> multiply -> inverse FFT -> extract)."""
+    FFT of rho, then per component IGF -> FFT -> multiply -> inverse FFT -> extract).
+
+    ``potential=True`` (EXTENSION, no reference counterpart -- parity unpinned): the same loop body run
+    once more with icomp = 0 -> potential_green_function, result stored in ``mesh.phi``."""
     T = mesh.T
     CT = np.complex64 if T == np.float32 else np.complex128
     nx, ny, nz = mesh.grid_size
@@ -287,25 +295,51 @@ def solve_freespace(mesh: Mesh3D, offset=(0.0, 0.0, 0.0)) -> None:
         temp = _fftn(temp, inverse=True).astype(CT, copy=False)  # :95
         mesh.efield[:, :, :, icomp - 1] = factr * temp.real[nx - 1:2 * nx - 1, ny - 1:2 * ny - 1,
                                                             nz - 1:2 * nz - 1].astype(T)  # :98-99
+    if potential:
+        cgrn = get_green_function((2 * nx, 2 * ny, 2 * nz), mesh.delta, mesh.gamma, 0, offset, T, potential_icomp0=True)
+        cgrn = _fftn(cgrn.astype(CT)).astype(CT, copy=False)
+        temp = _fftn((crho * cgrn).astype(CT, copy=False), inverse=True).astype(CT, copy=False)
+        mesh.phi = np.asfortranarray(factr * temp.real[nx - 1:2 * nx - 1, ny - 1:2 * ny - 1, nz - 1:2 * nz - 1].astype(T))
 
 
-def solve(mesh: Mesh3D, at_cathode: bool = False) -> None:
-    """solve!, src/solvers/free_space.jl:14-47."""
+def solve(mesh: Mesh3D, at_cathode: bool = False, potential: bool = False) -> None:
+    """solve!, src/solvers/free_space.jl:14-47.  ``potential``: extension, see solve_freespace."""
     T = mesh.T
-    solve_freespace(mesh, (T(0), T(0), T(0)))  # :17
+    solve_freespace(mesh, (T(0), T(0), T(0)), potential)  # :17
     if at_cathode:
         rho_img, e_img = _alloc(mesh.grid_size, T)
         image = Mesh3D(mesh.grid_size, mesh.min_bounds, mesh.max_bounds, mesh.delta, mesh.gamma,
                        mesh.total_charge, rho_img, e_img, T)
         image.rho[...] = -mesh.rho[:, :, ::-1]  # :34
         offset_z = T(T(2) * mesh.min_bounds[2] + T(mesh.max_bounds[2] - mesh.min_bounds[2]))  # :39
-        solve_freespace(image, (T(0), T(0), offset_z))  # :42
+        solve_freespace(image, (T(0), T(0), offset_z), potential)  # :42
         mesh.efield += image.efield  # :45
+        if potential:
+            mesh.phi += image.phi
+
+
+def magnetic_field(mesh: Mesh3D) -> np.ndarray:
+    """EXTENSION (no reference counterpart): B = (beta/c) z_hat x E for a bunch moving along +z."""
+    T = mesh.T
+    g = float(mesh.gamma)
+    boc = T(np.sqrt(1.0 - 1.0 / (g * g)) / CLIGHT)
+    b = np.zeros_like(mesh.efield)
+    b[..., 0] = -(boc * mesh.efield[..., 1])
+    b[..., 1] = boc * mesh.efield[..., 0]
+    return b
 
 
 # -------------------------------------------------------------------- interpolation
 def interpolate_field(mesh: Mesh3D, px, py, pz, clamp: bool = False):
-    """interpolate_field, src/interpolation.jl:100-128 with the kernel of :17-86.
+    """interpolate_field, src/interpolation.jl:100-128: the kernel's values stored into arrays of the
+    particles' element type (:110-112)."""
+    px = np.asarray(px)
+    P = px.dtype if px.dtype.kind == "f" else np.float64
+    return tuple(a.astype(P) for a in interpolate_field_promoted(mesh, px, py, pz, clamp))
+
+
+def interpolate_field_promoted(mesh: Mesh3D, px, py, pz, clamp: bool = False):
+    """interpolate_kernel!, src/interpolation.jl:17-86, values in promote(P, T) before the store.
 
     Weights (1-dx)*(1-dy)*(1-dz) ... left to right (:46-53); each component is the
     left-to-right sum of eight products in the order 000,100,010,110,001,101,011,111
@@ -331,7 +365,19 @@ def interpolate_field(mesh: Mesh3D, px, py, pz, clamp: bool = False):
                     w = ax[a] * ay[by] * az[cz]
                     term = e[ix + a, iy + by, iz + cz].astype(W) * w
                     acc = term if acc is None else acc + term
-        out.append(acc.astype(px.dtype if px.dtype.kind == "f" else np.float64))
+        out.append(acc)
+    return tuple(out)
+
+
+def interpolate_kick(mesh: Mesh3D, px, py, pz, mx, my, mz, coef_xy, coef_z, clamp: bool = False):
+    """EXTENSION (no reference counterpart): momenta after p += coef * E(particle), product and sum
+    rounded separately in promote(P, T), result cast to the particles' type."""
+    e = interpolate_field_promoted(mesh, px, py, pz, clamp)
+    W = e[0].dtype.type
+    P = np.asarray(px).dtype
+    out = []
+    for m, ec, c in zip((mx, my, mz), e, (coef_xy, coef_xy, coef_z)):
+        out.append((np.asarray(m).astype(W) + W(c) * ec).astype(P))
     return tuple(out)
 
 

@@ -23,6 +23,7 @@ from ._lib import LibraryMissing, ScbError  # noqa: F401
 
 __all__ = ["Mesh3D", "deposit_", "clear_mesh_", "interpolate_field", "solve_", "solve_freespace_",
            "get_green_function_", "cell_indices", "step_", "step_host_", "ErrorException", "CLIGHT", "FPEI",
+           "solve_potential_", "magnetic_field", "interpolate_kick_",
            "Handle", "default_handle"]
 
 CLIGHT = 299792458.0          # src/utils.jl:7
@@ -249,6 +250,7 @@ class Mesh3D:
         dev = "cuda:%d" % self.device
         self._rho = torch.zeros((nz, ny, nx), dtype=td, device=dev)
         self._efield = torch.zeros((3, nz, ny, nx), dtype=td, device=dev)
+        self._phi = None        # extension: allocated by solve_potential_
         self._workspace = None
 
     @staticmethod
@@ -300,6 +302,14 @@ class Mesh3D:
     @property
     def efield(self):
         return self._efield.permute(3, 2, 1, 0)
+
+    @property
+    def phi(self):
+        """Scalar potential (nx,ny,nz) written by ``solve_potential_`` (extension; the reference's
+        Mesh3D has no such field, src/mesh.jl:19-34)."""
+        if self._phi is None:
+            raise ErrorException("mesh.phi is only available after solve_potential_(mesh)")
+        return self._phi.permute(2, 1, 0)
 
     def __repr__(self):  # src/mesh.jl:240-246
         nx, ny, nz = self.grid_size
@@ -376,6 +386,52 @@ def solve_(mesh: Mesh3D, at_cathode: bool = False) -> None:
         return
     hd.check(hd.lib.scb_solve(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(),
                               mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0))
+
+
+def solve_potential_(mesh: Mesh3D, at_cathode: bool = False) -> None:
+    """Extension: ``solve!`` that also fills ``mesh.phi`` with the scalar potential,
+    computed with the reference's ``potential_green_function`` (src/green_functions.jl:13-22) as a fourth
+    component of the same fused convolution.  ``mesh.efield`` is written exactly as by ``solve_``."""
+    torch = _torch()
+    if mesh.sharded:
+        raise ErrorException("solve_potential_ is single-GPU (the slab-decomposed solve returns E only)")
+    hd = mesh.handle
+    hd.use_current_stream()
+    if mesh._phi is None:
+        mesh._phi = torch.zeros_like(mesh._rho)
+    hd.check(hd.lib.scb_solve_potential(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._phi.data_ptr(),
+                                        mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma),
+                                        1 if at_cathode else 0))
+
+
+def magnetic_field(mesh: Mesh3D):
+    """Extension: B = (beta/c) z_hat x E of a bunch moving along +z with ``mesh.gamma``; returns a
+    column-major (nx,ny,nz,3) view like ``mesh.efield``."""
+    torch = _torch()
+    hd = mesh.handle
+    hd.use_current_stream()
+    b = torch.empty_like(mesh._efield)
+    hd.check(hd.lib.scb_bfield(hd.h, mesh._efield.data_ptr(), b.data_ptr(), mesh._mdt(), mesh._n(), float(mesh.gamma)))
+    return b.permute(3, 2, 1, 0)
+
+
+def interpolate_kick_(mesh: Mesh3D, particles_x, particles_y, particles_z, px, py, pz, coef_xy: float, coef_z: float) -> None:
+    """Extension: ``interpolate_field`` fused with the momentum update
+    ``p += coef * E`` -- the interpolated field is never written to memory.  ``px, py, pz`` are CUDA
+    tensors of the particles' element type, updated in place."""
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    if not (x.dtype == y.dtype == z.dtype == px.dtype == py.dtype == pz.dtype):
+        raise ErrorException("particle arrays must share one element type")
+    if not (x.numel() == px.numel() == py.numel() == pz.numel()):
+        raise ErrorException("Particle coordinate and momentum arrays must have the same length.")
+    for p in (px, py, pz):
+        if p.device.type != "cuda" or not p.is_contiguous():
+            raise ErrorException("momentum arrays must be contiguous CUDA tensors (they are updated in place)")
+    hd.check(hd.lib.scb_interpolate_kick(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                         mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                         px.data_ptr(), py.data_ptr(), pz.data_ptr(), float(coef_xy), float(coef_z)))
 
 
 def solve_freespace_(mesh: Mesh3D, offset=(0.0, 0.0, 0.0)) -> None:

@@ -58,6 +58,10 @@ SIGNATURES = {
     "scb_deposit": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _I64x3, _F64x3, _F64x3, C.c_int]),
     "scb_solve": (C.c_int, [_vp, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _F64x3, C.c_double, C.c_int]),
     "scb_solve_freespace": (C.c_int, [_vp, _vp, _vp, C.c_int, _I64x3, _F64x3, C.c_double, _F64x3]),
+    "scb_solve_potential": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _F64x3, C.c_double, C.c_int]),
+    "scb_bfield": (C.c_int, [_vp, _vp, _vp, C.c_int, _I64x3, C.c_double]),
+    "scb_interpolate_kick": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
+                                       _vp, _vp, _vp, C.c_double, C.c_double]),
     "scb_interpolate": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _vp, _vp, _vp]),
     "scb_green": (C.c_int, [_vp, _vp, _I64x3, _F64x3, C.c_double, C.c_int, _F64x3, C.c_int]),
     "scb_bounds": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, _F64x3, _F64x3]),

@@ -45,6 +45,7 @@ struct GreenEntry {
     size_t bytes = 0;
     size_t cap = 0;       // allocated size (>= bytes when the buffer was recycled)
     long long scomp = 0;
+    int ncomp = 3;        // 3: Ex,Ey,Ez; 4: + potential (icomp 0) as component 3
     unsigned long long stamp = 0;
 };
 
@@ -267,21 +268,21 @@ int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const v
 
 // gather: repack the field node-major when there are enough particles to pay for the extra pass
 int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, const void* efield,
-                    int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready) {
+                    int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready, const Kick& kick = Kick()) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     const bool use_packed = (packed_ready && *packed_ready) || np * 4 >= ng;
     if (!use_packed) {
-        SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream));
+        SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick));
         h->launches += 1;
         return SCB_OK;
     }
     if (!(packed_ready && *packed_ready)) {
-        SCB_TRY(ensure_packed(h, (size_t)ng * 32));
+        SCB_TRY(ensure_packed(h, (size_t)ng * packed_bytes_per_node(mdt)));
         SCB_CUDA(h, launch_pack_efield(mdt, efield, h->packed, g, h->stream));
         h->launches += 1;
         if (packed_ready) *packed_ready = true;
     }
-    SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream));
+    SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream, kick));
     h->launches += 1;
     return SCB_OK;
 }
@@ -308,7 +309,7 @@ Plan make_plan(const int64_t n[3]) {
 }
 
 // ---- Green spectrum: build (cold) and cache ------------------------------------------------
-int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& ent) {
+int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& ent, int ncomp) {
     IgfGeom g{};
     for (int a = 0; a < 3; ++a) {
         g.n[a] = pl.n[a];
@@ -353,8 +354,9 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     if (prune) per_comp = (size_t)pl.PX * Lyh1 * Lzh1;
     else per_comp = nS;
     const size_t elem = (key.kind == 0 ? 1 : 2) * dt_size(key.mdt);
-    ent.bytes = 3 * per_comp * elem;
+    ent.bytes = (size_t)ncomp * per_comp * elem;
     ent.scomp = (long long)per_comp;
+    ent.ncomp = ncomp;
     // reuse a retired buffer when one is large enough: cudaFree/cudaMalloc of ~0.5 GB blocks costs
     // anything from 1 to 400 ms on the host and would dominate a re-mesh-every-step workload
     ent.data = nullptr;
@@ -388,8 +390,10 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     const bool foldZ = g.sym[2] && !g.corr[2];
     const int rowsY = foldY ? Lyh1 : pl.L[1];
     const int rowsZ = foldZ ? Lzh1 : pl.L[2];
-    for (int c = 0; c < 3; ++c) {
-        SCB_CUDA(h, launch_green_point(P, g, c + 1, h->stream));
+    for (int c = 0; c < ncomp; ++c) {
+        // components 0..2 = reference icomp 1..3 (src/green_functions.jl:90-98); component 3 = potential (icomp 0)
+        const int icomp = c < 3 ? c + 1 : 0;
+        SCB_CUDA(h, launch_green_point(P, g, icomp, h->stream));
         SCB_CUDA(h, launch_green_diff(Dd, P, g, h->stream));
         XParams<double> xp{};
         // the padded real array is generated inside the x pass (never written to memory)
@@ -398,7 +402,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
             xp.gen.n[a] = g.n[a]; xp.gen.L[a] = g.L[a]; xp.gen.sym[a] = g.sym[a]; xp.gen.corr[a] = g.corr[a];
             xp.gen.dcnt[a] = g.cnt[a] - 1;
         }
-        xp.gen.icomp = c + 1;
+        xp.gen.icomp = icomp;
         xp.gen.ly_lines = rowsY;
         xp.gen.sign_all = sign_all;
         xp.in = nullptr;
@@ -446,7 +450,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         const double2* final_spec = zdst;
         char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
         if (key.kind == 0)
-            SCB_CUDA(h, launch_green_compress_free(dst, f64, final_spec, pl.ninner, pl.PX, Lyh1, Lzh1, h->stream));
+            SCB_CUDA(h, launch_green_compress_free(dst, f64, final_spec, pl.ninner, pl.PX, Lyh1, Lzh1, icomp == 0, h->stream));
         else
             SCB_CUDA(h, launch_green_convert_full(dst, f64, final_spec, pl.ninner, pl.PX, (long long)per_comp, h->stream));
         h->launches += 7;
@@ -472,13 +476,20 @@ void free_green(scb_handle* h, bool release_pool) {
     }
 }
 
-int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEntry** out) {
+int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEntry** out, int ncomp = 3) {
     if (h->opt.green_cache) {
-        for (auto& e : h->green) {
+        for (size_t i = 0; i < h->green.size(); ++i) {
+            GreenEntry& e = h->green[i];
             if (e.key == key) {
-                e.stamp = ++h->stamp;
-                *out = &e;
-                return SCB_OK;
+                if (e.ncomp >= ncomp) {
+                    e.stamp = ++h->stamp;
+                    *out = &e;
+                    return SCB_OK;
+                }
+                // cached without the potential component: rebuild with it
+                retire_green(h, e);
+                h->green.erase(h->green.begin() + i);
+                break;
             }
         }
     } else {
@@ -503,7 +514,7 @@ int get_green(scb_handle* h, const Plan& pl, const GreenKey& key, const GreenEnt
     ent.key = key;
     ent.stamp = ++h->stamp;
     tick(h, 6);
-    int rc = build_green(h, pl, key, ent);
+    int rc = build_green(h, pl, key, ent, ncomp);
     tick(h, 7);
     h->t_green = true;
     if (rc != SCB_OK) {
@@ -531,32 +542,34 @@ GreenKey make_key(const Plan& pl, const double delta[3], double gamma, const dou
 
 // ---- the convolution -----------------------------------------------------------------------
 // mode 0: free space; mode 1: free space + cathode image (offset_z given); mode 2: general offset
+// phi (optional): scalar potential as a fourth component through the same passes (extension)
 template <typename T>
 int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const double delta[3], double gamma,
-              int mode, const double offset[3]) {
+              int mode, const double offset[3], T* phi = nullptr) {
     using C = cx_t<T>;
+    const int nc = phi ? 4 : 3;
     const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
     const double zero3[3] = {0, 0, 0};
     const GreenEntry* gfree = nullptr;
     const GreenEntry* gaux = nullptr;
     h->t_green = false;
     // the builds use the arena as scratch, so they must come before the passes touch it
-    if (mode == 0 || mode == 1) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, zero3, mdt, 0), &gfree));
+    if (mode == 0 || mode == 1) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, zero3, mdt, 0), &gfree, nc));
     if (mode == 1) {
-        SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 1), &gaux));
+        SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 1), &gaux, nc));
         // get_green may have reallocated the vector
         for (auto& e : h->green)
             if (e.key == make_key(pl, delta, gamma, zero3, mdt, 0)) gfree = &e;
     }
-    if (mode == 2) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 2), &gaux));
+    if (mode == 2) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 2), &gaux, nc));
 
     const size_t szA = (size_t)pl.PX * pl.n[1] * pl.n[2];
     const size_t szB = (size_t)pl.PX * pl.L[1] * pl.n[2];
-    SCB_TRY(ensure_arena(h, (4 * szA + 4 * szB) * sizeof(C)));
+    SCB_TRY(ensure_arena(h, ((1 + nc) * szA + (1 + nc) * szB) * sizeof(C)));
     C* A = static_cast<C*>(h->arena);
     C* B = A + szA;
     C* Cc = B + szB;
-    C* D = Cc + 3 * szB;
+    C* D = Cc + nc * szB;
 
     const C *twx, *twy, *twz;
     SCB_TRY(get_twiddles<T>(h, pl.L[0], &twx));
@@ -600,6 +613,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         p.tw = twz;
         p.out_scomp = (long long)szB;
         p.nz = pl.n[2];
+        p.ncomp = nc;
         p.ninner = pl.ninner;
         p.PX = pl.PX;
         p.Ly = pl.L[1];
@@ -632,7 +646,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         p.in_scomp = (long long)szB;
         p.out_scomp = (long long)szA;
         p.scale = (T)1;
-        SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, pl.n[2], 3, h->stream));
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, pl.n[2], nc, h->stream));
     }
     tick(h, 12);
     {  // B3
@@ -649,6 +663,12 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         // factr = T(FPEI) (src/solvers/free_space.jl:75) times the inverse-FFT 1/M (:95)
         p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
         SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
+        if (phi) {  // fourth component -> its own output array, same FPEI / M factor
+            p.in = D + 3 * szA;
+            p.out = phi;
+            SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 1, h->stream));
+            h->launches += 1;
+        }
     }
     tick(h, 13);
     h->t_pass = true;
@@ -657,7 +677,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
 }
 
 int solve_dispatch(scb_handle* h, const void* rho, void* efield, int mdt, const int64_t n[3], const double delta[3],
-                   double gamma, int mode, const double offset[3]) {
+                   double gamma, int mode, const double offset[3], void* phi = nullptr) {
     if (!h) return SCB_ERR_INVALID_ARG;
     if (!rho || !efield || !delta) return fail(h, SCB_ERR_INVALID_ARG, "null pointer argument");
     if (!valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad mesh dtype");
@@ -669,8 +689,8 @@ int solve_dispatch(scb_handle* h, const void* rho, void* efield, int mdt, const 
     const Plan pl = make_plan(n);
     tick(h, 2);
     int rc;
-    if (mdt == SCB_F64) rc = run_solve<double>(h, (const double*)rho, (double*)efield, pl, delta, gamma, mode, offset);
-    else rc = run_solve<float>(h, (const float*)rho, (float*)efield, pl, delta, gamma, mode, offset);
+    if (mdt == SCB_F64) rc = run_solve<double>(h, (const double*)rho, (double*)efield, pl, delta, gamma, mode, offset, (double*)phi);
+    else rc = run_solve<float>(h, (const float*)rho, (float*)efield, pl, delta, gamma, mode, offset, (float*)phi);
     tick(h, 3);
     h->t_solve = rc == SCB_OK;
     return rc;
@@ -853,6 +873,32 @@ int scb_solve_freespace(scb_handle* h, const void* rho, void* efield, int mdt, c
     return solve_dispatch(h, rho, efield, mdt, n, delta, gamma, zero ? 0 : 2, offset);
 }
 
+int scb_solve_potential(scb_handle* h, const void* rho, void* efield, void* phi, int mdt, const int64_t n[3],
+                        const double min_bounds[3], const double max_bounds[3], const double delta[3], double gamma,
+                        int at_cathode) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!min_bounds || !max_bounds || !phi) return fail(h, SCB_ERR_INVALID_ARG, "null bounds or phi");
+    double offset[3] = {0.0, 0.0, 0.0};
+    if (at_cathode) {
+        if (!valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad mesh dtype");
+        offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
+    }
+    return solve_dispatch(h, rho, efield, mdt, n, delta, gamma, at_cathode ? 1 : 0, offset, phi);
+}
+
+int scb_bfield(scb_handle* h, const void* efield, void* bfield, int mdt, const int64_t n[3], double gamma) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!efield || !bfield || !valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_bfield");
+    if (!(gamma >= 1.0)) return fail(h, SCB_ERR_INVALID_ARG, "gamma must be >= 1");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    // beta / c for a bunch moving along +z; formed in double, applied in the mesh precision
+    const double beta_over_c = std::sqrt(1.0 - 1.0 / (gamma * gamma)) / kCLight;
+    SCB_CUDA(h, launch_bfield(mdt, efield, bfield, (long long)n[0] * n[1] * n[2], beta_over_c, h->stream));
+    h->launches += 1;
+    return SCB_OK;
+}
+
 int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
                     const void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
                     const double delta[3], void* ex, void* ey, void* ez) {
@@ -864,6 +910,26 @@ int scb_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
     SCB_CUDA(h, cudaSetDevice(h->device));
     tick(h, 4);
     if (np > 0) SCB_TRY(run_interpolate(h, np, x, y, z, pdt, efield, mdt, make_geom(n, min_bounds, delta), ex, ey, ez, nullptr));
+    tick(h, 5);
+    h->t_interp = true;
+    return SCB_OK;
+}
+
+int scb_interpolate_kick(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
+                         const void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                         const double delta[3], void* px, void* py, void* pz, double coef_xy, double coef_z) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !efield || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_interpolate_kick");
+    if (np > 0 && (!x || !y || !z || !px || !py || !pz)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    Kick k;
+    k.on = 1;
+    k.cxy = coef_xy;
+    k.cz = coef_z;
+    tick(h, 4);
+    if (np > 0) SCB_TRY(run_interpolate(h, np, x, y, z, pdt, efield, mdt, make_geom(n, min_bounds, delta), px, py, pz, nullptr, k));
     tick(h, 5);
     h->t_interp = true;
     return SCB_OK;
@@ -989,7 +1055,7 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     bool packed_ready = false;
     if (np * 4 >= (int64_t)n[0] * n[1] * n[2]) {
-        SCB_TRY(ensure_packed(h, (size_t)n[0] * n[1] * n[2] * 32));
+        SCB_TRY(ensure_packed(h, (size_t)n[0] * n[1] * n[2] * packed_bytes_per_node(mdt)));
         SCB_CUDA(h, launch_pack_efield(mdt, efield, h->packed, g, h->stream));
         h->launches += 1;
         packed_ready = true;
@@ -1186,7 +1252,7 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
         ZParams<T> p{};
         p.in = RB; p.out = Cc; p.tw = twz;
         p.out_scomp = (long long)szB;
-        p.nz = pl.n[2]; p.ninner = pl.ninner; p.PX = pl.PX;
+        p.nz = pl.n[2]; p.ncomp = 3; p.ninner = pl.ninner; p.PX = pl.PX;
         p.Ly = Lyl; p.Lyg = pl.L[1]; p.ky0 = me * Lyl;
         p.S = static_cast<const T*>(gfree->data); p.S_scomp = gfree->scomp;
         if (gaux) { p.H = static_cast<const C*>(gaux->data); p.H_scomp = gaux->scomp; }

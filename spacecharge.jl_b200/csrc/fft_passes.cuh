@@ -131,6 +131,7 @@ struct ZParams {
     const cx_t<T>* tw;
     long long out_scomp;
     int nz;                 // valid z planes in and out
+    int ncomp;              // 3: Ex,Ey,Ez; 4: + scalar potential (component 3, even Green function => real spectrum)
     int ninner, PX, Ly;     // Ly: ky lines held by this rank (= plane pitch / PX)
     int Lyg, ky0;           // global padded y length and first global ky of this rank (Lyg = Ly, ky0 = 0 on one GPU)
     // peer-memory output (multi-GPU): z plane pos goes to rank pos / out_split through out_peer[rank],
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
     }
 
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < p.ncomp; ++c) {
         C w[8];
         if constexpr (USE_S) cp_async_wait_all();
 #pragma unroll
@@ -232,8 +233,8 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
                 if constexpr (USE_S) {
                     T s = sstage[q * SSTRIDE];
                     if ((c == 1 && ky > Lyh) || (c == 2 && kz > N / 2)) s = -s;
-                    // (a + ib) * (i s) = s * (-b + i a)
-                    acc = cmake<C>(-spec[q].y * s, spec[q].x * s);
+                    // field: (a + ib) * (i s) = s * (-b + i a);  potential: (a + ib) * s
+                    acc = c == 3 ? cmake<C>(spec[q].x * s, spec[q].y * s) : cmake<C>(-spec[q].y * s, spec[q].x * s);
                 }
                 if constexpr (KIND == GREEN_CATHODE) {
                     const int kzf = kz <= N / 2 ? kz : N - kz;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
             }
             w[q] = acc;
         }
-        if (c < 2) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
+        if (c + 1 < p.ncomp) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
         fft_line<T, N, +1>(w, lay, j, p.tw);
         const long long dst_off = c * p.out_scomp + (long long)kyl * p.PX + kx;
 #pragma unroll

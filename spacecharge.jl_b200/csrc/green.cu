@@ -22,6 +22,16 @@ __device__ __forceinline__ double field_green(double x, double y, double z) {
     return x * atan((y * z) / (r * x)) - z * log(r + y) + y * log((r - z) / (r + z)) / 2.0;
 }
 
+// src/green_functions.jl:13-22 (defined by the reference but unreachable from its solve!; used here for
+// the potential output, icomp = 0 -- SURVEY.md 8(f)-2)
+__device__ __forceinline__ double potential_green(double x, double y, double z) {
+    const double r = sqrt(x * x + y * y + z * z);
+    if (r == 0.0) return 0.0;
+    const double half = 0.5;
+    return -half * (z * z) * atan(x * y / (z * r)) - half * (y * y) * atan(x * z / (y * r)) -
+           half * (x * x) * atan(y * z / (x * r)) + y * z * log(x + r) + x * z * log(y + r) + x * y * log(z + r);
+}
+
 // Point-wise values P[mx + cx*(my + cy*mz)] for corner m <-> reference 1-based index i = i0 + m.
 // src/green_functions.jl:69-101
 __global__ void k_green_point(double* __restrict__ P, IgfGeom g, int icomp) {
@@ -43,6 +53,7 @@ __global__ void k_green_point(double* __restrict__ P, IgfGeom g, int icomp) {
     if (icomp == 1) gv = field_green(u, v, w) * factor;
     else if (icomp == 2) gv = field_green(v, w, u) * factor;
     else if (icomp == 3) gv = field_green(w, u, v) * factor;
+    else if (icomp == 0) gv = potential_green(u, v, w) * factor;   // extension: scalar potential
     else gv = 0.0;
     P[idx] = gv;
 }
@@ -87,11 +98,13 @@ __global__ void k_green_diff(double* __restrict__ D, const double* __restrict__ 
 // free space: Green_c = i*S_c, S_c real; the passes already pruned the spectrum to kx<=Lx/2,
 // ky<=Ly/2, kz<=Lz/2 (layout [kx][ky][kz], pitch PX), so this only takes the imaginary part
 template <typename T>
-__global__ void k_green_compress_free(T* __restrict__ S, const double2* __restrict__ spec, int ninner, int PX, long long total) {
+__global__ void k_green_compress_free(T* __restrict__ S, const double2* __restrict__ spec, int ninner, int PX, long long total,
+                                      int take_real) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int kx = (int)(idx % PX);
-    S[idx] = kx < ninner ? (T)spec[idx].y : (T)0;
+    // field components: odd along one axis => purely imaginary spectrum; potential: even => purely real
+    S[idx] = kx < ninner ? (T)(take_real ? spec[idx].x : spec[idx].y) : (T)0;
 }
 
 template <typename T>
@@ -125,10 +138,11 @@ cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1, cudaStream_t s) {
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1,
+                                       int take_real, cudaStream_t s) {
     const long long total = (long long)PX * Lyh1 * Lzh1;
-    if (dt_f64) k_green_compress_free<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)S, spec, ninner, PX, total);
-    else k_green_compress_free<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, ninner, PX, total);
+    if (dt_f64) k_green_compress_free<double><<<blocks_for(total, 256), 256, 0, s>>>((double*)S, spec, ninner, PX, total, take_real);
+    else k_green_compress_free<float><<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, ninner, PX, total, take_real);
     return cudaGetLastError();
 }
 

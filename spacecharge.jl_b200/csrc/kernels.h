@@ -23,12 +23,19 @@ struct Geom3 {
     int n[3];
 };
 
+// fused momentum kick of the gather kernels: off = plain interpolate_field (outputs overwritten)
+struct Kick {
+    int on = 0;
+    double cxy = 0.0, cz = 0.0;   // p_{x,y} += cxy * E_{x,y},  p_z += cz * E_z
+};
+
 // green.cu
 cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStream_t s);
 cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s);
 // D: the differenced values, (cnt-1)^3 doubles
 cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cudaStream_t s);
-cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1, cudaStream_t s);
+cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1,
+                                       int take_real, cudaStream_t s);
 cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, int ninner, int PX, long long total, cudaStream_t s);
 
 // particles.cu  (pdt/mdt: 0 = f32, 1 = f64)
@@ -40,11 +47,15 @@ cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const 
 cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                  const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
+                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
+                               const Kick& kick = Kick());
 // node-major repack of efield (32 bytes per node) and the gather that reads it
+size_t packed_bytes_per_node(int mdt);   // node-major record size
 cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s);
 cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                                      const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s);
+                                      const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
+                                      const Kick& kick = Kick());
+cudaError_t launch_bfield(int mdt, const void* efield, void* bfield, long long ng, double beta_over_c, cudaStream_t s);
 cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                               const Geom3& g, long long* ix, long long* iy, long long* iz, cudaStream_t s);
 // partial[0..2] = min, partial[3..5] = max as doubles; must be initialised by the launcher

@@ -181,12 +181,21 @@ __global__ void __launch_bounds__(256) k_fold_tiles(const T* __restrict__ tiles,
     rho[idx] = accumulate ? rho[idx] + s : s;
 }
 
+// Result store shared by the gather kernels.  Plain interpolation writes the field value; the fused
+// momentum kick updates the caller's array in place, p <- p + coef * E, with the
+// product and the sum formed separately in W (no contraction: -fmad=false) and rounded to P once.
+template <typename P, typename W>
+__device__ __forceinline__ void put_result(P* __restrict__ arr, long long i, W val, const Kick& k, bool is_z) {
+    if (k.on) val = (W)arr[i] + (W)(is_z ? k.cz : k.cxy) * val;
+    st_stream(arr + i, (P)val);
+}
+
 // ---- interpolate: one thread per particle, 24 gathers --------------------------------------
 template <typename P, typename T>
 __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                       const P* __restrict__ z, const T* __restrict__ e,
                                                       const Geom3 g, P* __restrict__ ex, P* __restrict__ ey,
-                                                      P* __restrict__ ez) {
+                                                      P* __restrict__ ez, const Kick kick) {
     using W = typename promote<P, T>::type;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1], sc = sz * g.n[2];
@@ -214,9 +223,9 @@ __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __re
                      (W)__ldg(bk + sy + 1) * w110 + (W)__ldg(bk + sz) * w001 + (W)__ldg(bk + sz + 1) * w101 +
                      (W)__ldg(bk + sz + sy) * w011 + (W)__ldg(bk + sz + sy + 1) * w111;
         }
-        st_stream(ex + i, (P)out[0]);
-        st_stream(ey + i, (P)out[1]);
-        st_stream(ez + i, (P)out[2]);
+        put_result<P, W>(ex, i, out[0], kick, false);
+        put_result<P, W>(ey, i, out[1], kick, false);
+        put_result<P, W>(ez, i, out[2], kick, true);
     }
 }
 
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f64(long long np, co
                                                                  const P* __restrict__ y, const P* __restrict__ z,
                                                                  const double4* __restrict__ e, const Geom3 g,
                                                                  P* __restrict__ ex, P* __restrict__ ey,
-                                                                 P* __restrict__ ez) {
+                                                                 P* __restrict__ ez, const Kick kick) {
     using W = double;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
@@ -291,9 +300,9 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f64(long long np, co
         for (int k = 0; k < 3; ++k)
             out[k] = n000[k] * w000 + n100[k] * w100 + n010[k] * w010 + n110[k] * w110 + n001[k] * w001 +
                      n101[k] * w101 + n011[k] * w011 + n111[k] * w111;
-        st_stream(ex + i, (P)out[0]);
-        st_stream(ey + i, (P)out[1]);
-        st_stream(ez + i, (P)out[2]);
+        put_result<P, W>(ex, i, out[0], kick, false);
+        put_result<P, W>(ey, i, out[1], kick, false);
+        put_result<P, W>(ez, i, out[2], kick, true);
     }
 }
 
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
                                                                const P* __restrict__ y, const P* __restrict__ z,
                                                                const double4* __restrict__ e, const Geom3 g,
                                                                P* __restrict__ ex, P* __restrict__ ey,
-                                                               P* __restrict__ ez) {
+                                                               P* __restrict__ ez, const Kick kick) {
     using W = double;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -358,9 +367,9 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
             }
         }
         if (i < np) {
-            st_stream(ex + i, (P)mine[0]);
-            st_stream(ey + i, (P)mine[1]);
-            st_stream(ez + i, (P)mine[2]);
+            put_result<P, W>(ex, i, mine[0], kick, false);
+            put_result<P, W>(ey, i, mine[1], kick, false);
+            put_result<P, W>(ez, i, mine[2], kick, true);
         }
     }
 }
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
                                                                  const P* __restrict__ y, const P* __restrict__ z,
                                                                  const float4* __restrict__ e, const Geom3 g,
                                                                  P* __restrict__ ex, P* __restrict__ ey,
-                                                                 P* __restrict__ ez) {
+                                                                 P* __restrict__ ez, const Kick kick) {
     using W = typename promote<P, float>::type;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
@@ -397,10 +406,22 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
         for (int k = 0; k < 3; ++k)
             out[k] = (W)p00[k] * w000 + (W)p00[4 + k] * w100 + (W)p10[k] * w010 + (W)p10[4 + k] * w110 +
                      (W)p01[k] * w001 + (W)p01[4 + k] * w101 + (W)p11[k] * w011 + (W)p11[4 + k] * w111;
-        st_stream(ex + i, (P)out[0]);
-        st_stream(ey + i, (P)out[1]);
-        st_stream(ez + i, (P)out[2]);
+        put_result<P, W>(ex, i, out[0], kick, false);
+        put_result<P, W>(ey, i, out[1], kick, false);
+        put_result<P, W>(ez, i, out[2], kick, true);
     }
+}
+
+// ---- magnetic field of a bunch moving along +z (extension) -----------------
+// B = (beta/c) z_hat x E:  Bx = -(beta/c) Ey,  By = (beta/c) Ex,  Bz = 0   (same SoA layout as efield)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bfield(const T* __restrict__ e, T* __restrict__ b, long long ng, T boc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ng) return;
+    const T ex = ld_stream(e + i), ey = ld_stream(e + ng + i);
+    b[i] = -(boc * ey);
+    b[ng + i] = boc * ex;
+    b[2 * ng + i] = (T)0;
 }
 
 // ---- parity hook: unclamped cell indices ----------------------------------------------------
@@ -487,10 +508,11 @@ cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const 
 }
 
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s) {
+                               const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
+                               const Kick& kick) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
-#define CALL(P, T) k_interpolate<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez);
+#define CALL(P, T) k_interpolate<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick);
     SCB_DISPATCH_PT(CALL)
 #undef CALL
     return cudaGetLastError();
@@ -513,6 +535,13 @@ cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, 
     return cudaGetLastError();
 }
 
+int interp_mode() {
+    static const int m = [] { const char* e = getenv("SCB_INTERP_MODE"); return e ? atoi(e) : 0; }();
+    return m;
+}
+
+size_t packed_bytes_per_node(int) { return 32; }
+
 cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     const unsigned grid = (unsigned)((ng + 255) / 256);
@@ -522,20 +551,29 @@ cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const 
 }
 
 cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                                      const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s) {
+                                      const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
+                                      const Kick& kick) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
-    static const bool thread_per_particle = [] { const char* e = getenv("SCB_INTERP_MODE"); return e && atoi(e) == 1; }();
+    static const int imode = interp_mode();
+    const bool thread_per_particle = imode == 1;
     if (mdt == 1 && thread_per_particle) {
-        if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
-        else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
+        if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
+        else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else if (mdt == 1) {
-        if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
-        else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
+        if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
+        else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else {
-        if (pdt == 1) k_interpolate_packed_f32<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez);
-        else k_interpolate_packed_f32<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez);
+        if (pdt == 1) k_interpolate_packed_f32<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
+        else k_interpolate_packed_f32<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bfield(int mdt, const void* efield, void* bfield, long long ng, double beta_over_c, cudaStream_t s) {
+    const unsigned grid = (unsigned)((ng + 255) / 256);
+    if (mdt == 1) k_bfield<double><<<grid, 256, 0, s>>>((const double*)efield, (double*)bfield, ng, beta_over_c);
+    else k_bfield<float><<<grid, 256, 0, s>>>((const float*)efield, (float*)bfield, ng, (float)beta_over_c);
     return cudaGetLastError();
 }
 

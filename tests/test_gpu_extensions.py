@@ -1,0 +1,118 @@
+"""GPU parity of the extension entry points with the oracle's restatement:
+scb_solve_potential (phi through the fused passes as a fourth component), scb_bfield, scb_interpolate_kick.
+The reference has no counterpart (src/mesh.jl:19-34 stores rho and efield only), so the oracle functions
+used here are themselves pinned by tests/test_oracle_extensions.py (direct summation, analytic Gaussian,
+E = -grad phi)."""
+import math
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import TOL32, TOL64, check, gaussian, set_rho, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(scb, oracle, grid, lo, hi, gamma, rho, T=np.float64):
+    ref = oracle.mesh_from_bounds(grid, lo, hi, T=np.float64, gamma=gamma)
+    mesh = scb.Mesh3D(grid, lo, hi, T=T, gamma=gamma)
+    if T == np.float32:
+        ref.min_bounds, ref.max_bounds, ref.delta = (tuple(np.float64(v) for v in t)
+                                                     for t in (mesh.min_bounds, mesh.max_bounds, mesh.delta))
+    ref.rho[...] = rho.astype(T)
+    set_rho(mesh, rho.astype(T))
+    return mesh, ref
+
+
+@pytest.mark.parametrize("grid", [(8, 8, 8), (6, 10, 5), (2, 3, 4), (33, 17, 40), (32, 32, 32)])
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_potential_matches_oracle_f64(scb, oracle, record, grid, at_cathode):
+    rng = np.random.default_rng(sum(grid) + 1)
+    rho = rng.standard_normal(grid)
+    mesh, ref = _pair(scb, oracle, grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), 3.0, rho)
+    oracle.solve(ref, at_cathode=at_cathode, potential=True)
+    scb.solve_potential_(mesh, at_cathode=at_cathode)
+    check(record, "phi", mesh.phi.cpu().numpy(), ref.phi, TOL64)
+    got = mesh.efield.cpu().numpy()
+    for c in range(3):
+        check(record, "E%d" % c, got[..., c], ref.efield[..., c], TOL64)
+
+
+def test_potential_f32_and_cache_upgrade(scb, oracle, record):
+    """A plain solve_ first (3-component spectrum cached), then solve_potential_ on the same geometry:
+    the cached entry must be rebuilt with the potential component, and E must not change."""
+    grid = (16, 24, 32)
+    rng = np.random.default_rng(8)
+    rho = rng.standard_normal(grid)
+    mesh, ref = _pair(scb, oracle, grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), 2.0, rho, T=np.float32)
+    oracle.solve(ref, potential=True)
+    scb.solve_(mesh)
+    e0 = mesh.efield.clone()
+    scb.solve_potential_(mesh)
+    assert bool((mesh.efield == e0).all())
+    check(record, "phi f32", mesh.phi.cpu().numpy(), ref.phi, TOL32)
+    scb.solve_(mesh)       # and back: the 4-component entry serves the plain solve
+    assert bool((mesh.efield == e0).all())
+    with pytest.raises(scb.ErrorException):
+        scb.Mesh3D(grid, (-1, -1, -1), (1, 1, 1)).phi
+
+
+def test_potential_of_gaussian_bunch_on_gpu(scb, record):
+    """Full path (deposit + solve_potential_) against the analytic potential of an isotropic Gaussian."""
+    n, sigma, Q = 1_000_000, 1e-3, 1e-9
+    x, y, z, q = gaussian(n, 123, sigma, Q)
+    d = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D((64, 64, 64), *d[:3])
+    scb.deposit_(mesh, *d)
+    scb.solve_potential_(mesh)
+    ax = [mesh.min_bounds[a] + mesh.delta[a] * np.arange(64) for a in range(3)]
+    X, Y, Z = np.meshgrid(*ax, indexing="ij")
+    r = np.sqrt(X * X + Y * Y + Z * Z)
+    want = scb.FPEI * Q * np.vectorize(math.erf)(r / (math.sqrt(2) * sigma)) / r
+    err = np.abs(mesh.phi.cpu().numpy() - want).max() / np.abs(want).max()
+    record("phi vs analytic Gaussian 64^3", err, 0.02)
+    assert err < 0.02
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_magnetic_field(scb, oracle, T):
+    import torch
+    grid = (9, 7, 11)
+    rng = np.random.default_rng(4)
+    e = rng.standard_normal(grid + (3,)).astype(T)
+    ref = oracle.mesh_from_bounds(grid, (-1, -1, -1), (1, 1, 1), T=T, gamma=7.0)
+    mesh = scb.Mesh3D(grid, (-1, -1, -1), (1, 1, 1), T=T, gamma=7.0)
+    ref.efield[...] = e
+    mesh.efield.copy_(torch.from_numpy(e).cuda())
+    got = scb.magnetic_field(mesh).cpu().numpy()
+    assert np.array_equal(got, oracle.magnetic_field(ref))
+
+
+@pytest.mark.parametrize("pdt,mdt,tol", [(np.float64, np.float64, 1e-13), (np.float32, np.float32, TOL32),
+                                         (np.float64, np.float32, TOL32), (np.float32, np.float64, 1e-6)])
+@pytest.mark.parametrize("n", [50000, 300])          # packed-field gather / 24-gather kernel
+def test_interpolate_kick_matches_oracle(scb, oracle, record, pdt, mdt, tol, n):
+    import torch
+    x, y, z, q = gaussian(n, 19, dtype=pdt)
+    grid = (20, 31, 16)
+    ref = oracle.mesh_from_particles(grid, x, y, z, T=mdt)
+    mesh = scb.Mesh3D(grid, *to_dev(x, y, z), T=mdt)
+    rng = np.random.default_rng(6)
+    e = rng.standard_normal(grid + (3,)).astype(mdt)
+    ref.efield[...] = e
+    mesh.efield.copy_(torch.from_numpy(e).cuda())
+    p0 = [rng.standard_normal(n).astype(pdt) for _ in range(3)]
+    want = oracle.interpolate_kick(ref, x, y, z, *p0, 0.37, -1.9, clamp=True)
+    mom = list(to_dev(*p0))
+    scb.interpolate_kick_(mesh, *to_dev(x, y, z), *mom, 0.37, -1.9)
+    for g, w, p in zip(mom, want, p0):
+        assert g.dtype == (torch.float32 if pdt == np.float32 else torch.float64)
+        # graded on the increment, which is what the kernel computes
+        check(record, "kick", g.cpu().numpy().astype(np.float64) - p, w.astype(np.float64) - p, max(tol, 1e-6 if pdt == np.float32 else tol))
+    # the kick with the same coefficients equals interpolate_field followed by the update
+    ex, ey, ez = scb.interpolate_field(mesh, *to_dev(x, y, z))
+    mom2 = list(to_dev(*p0))
+    scb.interpolate_kick_(mesh, *to_dev(x, y, z), *mom2, 1.0, 1.0)
+    for g, p, ec in zip(mom2, p0, (ex, ey, ez)):
+        assert np.array_equal(g.cpu().numpy(), (p.astype(np.float64) + ec.cpu().numpy().astype(np.float64)).astype(pdt)) or \
+            np.abs(g.cpu().numpy() - (p + ec.cpu().numpy())).max() <= 4 * np.finfo(pdt).eps * np.abs(p + ec.cpu().numpy()).max()
