@@ -540,6 +540,41 @@ GreenKey make_key(const Plan& pl, const double delta[3], double gamma, const dou
     return k;
 }
 
+// ---- tensor maps for the TMA variant of the fused z pass ---------------------------------------
+typedef CUresult (*scb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+scb_encode_tiled_fn tensor_map_encoder() {
+    static scb_encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<scb_encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+
+// dims / box in elements (innermost first), strides in bytes for dims 1..rank-1
+bool make_tensor_map(CUtensorMap* m, bool f64, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box) {
+    scb_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    return enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+               const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool z_tma_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SCB_Z_TMA"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
 // ---- the convolution -----------------------------------------------------------------------
 // mode 0: free space; mode 1: free space + cathode image (offset_z given); mode 2: general offset
 // phi (optional): scalar potential as a fourth component through the same passes (extension)
@@ -628,7 +663,30 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
             p.H_scomp = gaux->scomp;
         }
         const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
-        SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
+        bool done = false;
+        if (mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
+            // all global traffic of the pass through the TMA unit (see k_z_tma)
+            const bool f64 = sizeof(T) == 8;
+            const cuuint64_t s = sizeof(T), PX = pl.PX, L1 = pl.L[1], nz = pl.n[2];
+            const cuuint32_t TX = (cuuint32_t)tz_for(pl.L[2]);
+            const cuuint64_t Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
+            CUtensorMap mB, mC, mS;
+            const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
+            const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
+            const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)szB * 2 * s};
+            const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
+            const cuuint64_t dS[4] = {PX, Lyh1, Lzh1, (cuuint64_t)gfree->ncomp},
+                             sS[3] = {PX * s, PX * Lyh1 * s, (cuuint64_t)gfree->scomp * s};
+            const cuuint32_t bS[4] = {TX, 1, (cuuint32_t)z_tma_srows<T>(pl.L[2]), 1};
+            if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC) &&
+                make_tensor_map(&mS, f64, 4, gfree->data, dS, sS, bS)) {
+                cudaError_t e = launch_z_tma<T>(pl.L[2], p, mB, mC, mS, h->stream);
+                if (e == cudaSuccess) done = true;
+                else if (e != cudaErrorNotSupported) return cuda_fail(h, e, "launch_z_tma");
+                else (void)cudaGetLastError();
+            }
+        }
+        if (!done) SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
     }
     tick(h, 11);
     {  // B2

@@ -17,6 +17,7 @@
 // replaces: src/solvers/free_space.jl:68-99 (fill!, embed, 7 in-place C2C FFTs, multiply,
 // scale, extract) of the reference.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved at run time in api.cu)
 #include "fft_engine.cuh"
 
 namespace scb {
@@ -266,6 +267,165 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fused z pass, TMA variant (free space, single GPU, nz <= 256)
+//
+// ncu on k_z_fused (config 5, Float64): the LSU data pipe is the busiest unit (71 % of its wavefront rate): 72 % of
+// the wavefronts are the shared-memory exchanges of the four transforms, the rest are the strided global loads and
+// stores (64-byte segments) and the 8-byte cp.async prefetches of the Green spectrum, each of which costs a
+// wavefront per 32-byte sector.  Here all global traffic goes through the TMA unit instead: one bulk tensor load
+// brings the TX x nz input tile, two bring the folded Green-spectrum rows of a component (double-buffered one
+// component ahead), and each component's TX x nz output tile leaves with one bulk tensor store from a staging
+// buffer -- the LSU only carries the exchanges.  Out-of-range rows/columns are zero-filled on load and clipped on
+// store by the tensor maps, so the padding costs no instructions.
+//   mapB: rank 3 {2*PX, Ly, nz} of T, box {2*TX, 1, nz};  mapC: rank 4 {2*PX, Ly, nz, ncomp}, box {2*TX, 1, nz, 1};
+//   mapS: rank 4 {PX, Ly/2+1, Lz/2+1, ncomp}, box {TX, 1, SR, 1}, SR = z_tma_srows (two boxes per component)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3, const void* src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(K) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
+// Box rows of the Green-spectrum tensor map for padded length N: two boxes cover kz' = 0..N/2, and a box must be a
+// multiple of 128 bytes so that the second one lands on a 128-byte aligned shared-memory address (TMA requirement).
+template <typename T> __host__ __device__ constexpr int z_tma_srows(int N) {
+    const int row = tz_for(N) * (int)sizeof(T);
+    const int q = row >= 128 ? 1 : 128 / row;
+    return ((N / 2 + 2) / 2 + q - 1) / q * q;
+}
+
+template <typename T, int N>
+struct ZTmaLayout {
+    using C = cx_t<T>;
+    static constexpr int TX = tz_for(N);
+    static constexpr int SR = z_tma_srows<T>(N);                                // rows per Green-spectrum box
+    static constexpr size_t EX = round128(LayoutRows<C, TX>::bytes(N));         // exchange buffer
+    static constexpr size_t TILE = round128((size_t)(N / 2) * TX * sizeof(C));  // input tile / output staging
+    static constexpr size_t SB = round128((size_t)2 * SR * TX * sizeof(T));     // one component's spectrum rows
+    static constexpr size_t BARS = EX + 2 * TILE + 2 * SB;
+    static constexpr size_t BYTES = BARS + 64;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>())
+k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+        const __grid_constant__ CUtensorMap mapS, const ZParams<T> p) {
+    using C = cx_t<T>;
+    using LY = ZTmaLayout<T, N>;
+    constexpr int TX = LY::TX;
+    constexpr int TPL = N / 8;
+    constexpr int SR = LY::SR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tx = threadIdx.x, j = threadIdx.y;
+    const bool leader = (tx == 0 && j == 0);
+    const int kx0 = blockIdx.x * TX;
+    int kyl = blockIdx.y;   // ky / Ly-ky back to back: they read the same folded spectrum rows (L2 reuse)
+    {
+        const int b = blockIdx.y, m = b >> 1;
+        kyl = b == 0 ? 0 : b == 1 ? p.Ly / 2 : (b & 1) ? p.Ly - m : m;
+    }
+    const int ky = kyl;
+    const int Lyh = p.Ly / 2;
+    const int kyf = ky <= Lyh ? ky : p.Ly - ky;
+    LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
+    auto tile = [&](int b) { return reinterpret_cast<C*>(smem_raw + LY::EX + (size_t)b * LY::TILE); };
+    auto sbuf = [&](int b) { return reinterpret_cast<T*>(smem_raw + LY::EX + 2 * LY::TILE + (size_t)b * LY::SB); };
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + LY::BARS);   // [0] input, [1],[2] spectrum
+    const unsigned tile_bytes = (unsigned)p.nz * TX * sizeof(C);
+    const unsigned s_bytes = 2u * SR * TX * sizeof(T);
+
+    auto load_S = [&](int c) {   // leader only
+        unsigned long long* bar = bars + 1 + (c & 1);
+        mbar_expect_tx(bar, s_bytes);
+        tma_load_4d(sbuf(c & 1), &mapS, kx0, kyf, 0, c, bar);
+        tma_load_4d(sbuf(c & 1) + SR * TX, &mapS, kx0, kyf, SR, c, bar);
+    };
+
+    if (leader) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        mbar_init(bars + 2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (leader) {
+        mbar_expect_tx(bars + 0, tile_bytes);
+        tma_load_3d(tile(0), &mapB, 2 * kx0, kyl, 0, bars + 0);
+        load_S(0);
+        if (p.ncomp > 1) load_S(1);
+    }
+
+    C spec[8];
+    mbar_wait(bars + 0, 0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = j + q * TPL;
+        spec[q] = (q < 4 && pos < p.nz) ? tile(0)[pos * TX + tx] : cmake<C>(0, 0);
+    }
+    fft_line<T, N, -1>(spec, lay, j, p.tw);
+
+#pragma unroll 1
+    for (int c = 0; c < p.ncomp; ++c) {
+        C w[8];
+        mbar_wait(bars + 1 + (c & 1), (c >> 1) & 1);
+        const T* sb = sbuf(c & 1) + tx;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int kz = j + q * TPL;
+            const int kzf = kz <= N / 2 ? kz : N - kz;
+            T s = sb[kzf * TX];
+            if ((c == 1 && ky > Lyh) || (c == 2 && kz > N / 2)) s = -s;
+            // field: (a + ib) * (i s) = s * (-b + i a);  potential: (a + ib) * s
+            w[q] = c == 3 ? cmake<C>(spec[q].x * s, spec[q].y * s) : cmake<C>(-spec[q].y * s, spec[q].x * s);
+        }
+        fft_line<T, N, +1>(w, lay, j, p.tw);
+        // staging buffer c&1 was handed to the store of component c-2 (c = 0 reuses the input tile, which every thread
+        // finished reading before the first barrier of the forward transform)
+        if (c >= 2 && leader) bulk_wait_read<1>();
+        if (c >= 2 || N < 16) __syncthreads();
+        C* ob = tile(c & 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pos = j + q * TPL;
+            if (pos < p.nz) ob[pos * TX + tx] = w[q];
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (leader) {
+            tma_store_4d(&mapC, 2 * kx0, kyl, 0, c, ob);
+            bulk_commit();
+            if (c + 2 < p.ncomp) load_S(c + 2);   // everyone is past its reads of sbuf[c&1] (barrier above)
+        }
+    }
+    if (leader) bulk_wait_read<0>();   // shared memory must outlive the stores that read it
+}
+
 // ------------------------------------------------------------------------------------------
 // x passes: real <-> half-complex along the contiguous axis, two real lines per transform
 // Generator for the x pass of the Green-spectrum build: the padded, wrap-around-placed IGF array is
@@ -439,6 +599,10 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> 
 // host-side launchers (defined per precision in fft_passes_f32.cu / fft_passes_f64.cu)
 template <typename T> cudaError_t launch_lines(int N, int dir, const LinesParams<T>& p, int nouter, int ncomp, cudaStream_t s);
 template <typename T> cudaError_t launch_z_fused(int N, int kind, const ZParams<T>& p, cudaStream_t s);
+// TMA variant; returns cudaErrorNotSupported when this (N, nz) has no TMA instantiation
+template <typename T> cudaError_t launch_z_tma(int N, const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC,
+                                                const CUtensorMap& mapS, cudaStream_t s);
+
 template <typename T> cudaError_t launch_x_r2c(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 template <typename T> cudaError_t launch_x_c2r(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 bool fft_len_supported(int N);

@@ -57,6 +57,21 @@ template <> cudaError_t launch_z_fused<SCB_T>(int N, int kind, const ZParams<SCB
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC,
+                                             const CUtensorMap& mapS, cudaStream_t s) {
+    cudaError_t e = cudaErrorNotSupported;
+#define X(NN)                                                                                     \
+    if (N == NN) {                                                                                \
+        using LY = ZTmaLayout<SCB_T, NN>;                                                         \
+        dim3 grid((p.ninner + LY::TX - 1) / LY::TX, p.Ly), block(LY::TX, NN / 8);                 \
+        e = set_smem(k_z_tma<SCB_T, NN>, LY::BYTES);                                              \
+        if (e == cudaSuccess) k_z_tma<SCB_T, NN><<<grid, block, LY::BYTES, s>>>(mapB, mapC, mapS, p); \
+    }
+    X(16) X(32) X(64) X(128) X(256) X(512)
+#undef X
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 template <> cudaError_t launch_x_r2c<SCB_T>(int N, const XParams<SCB_T>& p, int ncomp, cudaStream_t s) {
     using C = cx_t<SCB_T>;
     cudaError_t e = cudaErrorInvalidValue;
