@@ -565,9 +565,12 @@ bool make_tensor_map(CUtensorMap* m, bool f64, int rank, const void* base, const
     scb_encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    static const int promo = [] { const char* e = std::getenv("SCB_TMA_L2"); return e ? std::atoi(e) : 0; }();   // tuning knob
+    const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     return enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool z_tma_enabled() {

@@ -85,10 +85,41 @@ struct LayoutLine {
     __host__ __device__ static constexpr int row(int N) { return N + N / 8 + 1; }
 };
 
+// ---- per-thread twiddle registers --------------------------------------------------------------
+// The twiddles a thread needs depend only on its position j in the line, not on the data: stage Ns uses
+// w1 = root^t, w2 = root^2t, w4 = root^4t (radix 8) with t = (jp mod Ns) * N/(Ns*R).  ncu on the fused z pass
+// showed these table loads as the largest stall reason (long scoreboard) and ~18 % of the LSU wavefronts, so only
+// w1 is fetched -- once per thread, before the first transform, and kept in registers across all transforms of
+// the kernel -- and w2 = w1^2, w4 = w2^2 are formed in registers (a few ulp, far below the parity bar).
+template <int N, int Ns = 1> __host__ __device__ constexpr int tw_count() {
+    constexpr int REM = N / Ns;
+    constexpr int R = REM >= 8 ? 8 : REM;
+    constexpr int G = 8 / R;
+    if constexpr (Ns * R < N) return (Ns > 1 ? G : 0) + tw_count<N, Ns * R>();
+    else return Ns > 1 ? G : 0;
+}
+
+template <typename T, int N, int Ns = 1, int OFF = 0>
+__device__ __forceinline__ void fft_twiddles(cx_t<T> (&w)[tw_count<N>() > 0 ? tw_count<N>() : 1], const int j,
+                                             const cx_t<T>* __restrict__ tw) {
+    constexpr int TPL = N / 8;
+    constexpr int REM = N / Ns;
+    constexpr int R = REM >= 8 ? 8 : REM;
+    constexpr int G = 8 / R;
+    if constexpr (Ns > 1) {
+#pragma unroll
+        for (int m = 0; m < G; ++m) {
+            const int jp = j + m * TPL;
+            w[OFF + m] = __ldg(tw + (jp & (Ns - 1)) * (N / (Ns * R)));
+        }
+    }
+    if constexpr (Ns * R < N) fft_twiddles<T, N, Ns * R, OFF + (Ns > 1 ? G : 0)>(w, j, tw);
+}
+
 // ---- one Stockham stage (recursive over Ns) ----------------------------------------------
-template <typename T, int N, int DIR, int Ns, typename Lay>
+template <typename T, int N, int DIR, int Ns, int OFF, typename Lay>
 __device__ __forceinline__ void fft_stage(cx_t<T> (&v)[8], const Lay& lay, const int j,
-                                          const cx_t<T>* __restrict__ tw) {
+                                          const cx_t<T> (&wr)[tw_count<N>() > 0 ? tw_count<N>() : 1]) {
     using C = cx_t<T>;
     constexpr int TPL = N / 8;
     constexpr int REM = N / Ns;
@@ -98,13 +129,11 @@ __device__ __forceinline__ void fft_stage(cx_t<T> (&v)[8], const Lay& lay, const
 
 #pragma unroll
     for (int m = 0; m < G; ++m) {
-        const int jp = j + m * TPL;
         if constexpr (Ns > 1) {
-            const int t = (jp & (Ns - 1)) * (N / (Ns * R));
+            const C w1 = tw_dir<DIR>(wr[OFF + m]);
             if constexpr (R == 8) {
-                const C w1 = tw_dir<DIR>(__ldg(tw + t));
-                const C w2 = tw_dir<DIR>(__ldg(tw + 2 * t));
-                const C w4 = tw_dir<DIR>(__ldg(tw + 4 * t));
+                const C w2 = cmul(w1, w1);
+                const C w4 = cmul(w2, w2);
                 const C w3 = cmul(w1, w2);
                 v[m + 1 * G] = cmul(v[m + 1 * G], w1);
                 v[m + 2 * G] = cmul(v[m + 2 * G], w2);
@@ -114,13 +143,11 @@ __device__ __forceinline__ void fft_stage(cx_t<T> (&v)[8], const Lay& lay, const
                 v[m + 6 * G] = cmul(v[m + 6 * G], cmul(w4, w2));
                 v[m + 7 * G] = cmul(v[m + 7 * G], cmul(w4, w3));
             } else if constexpr (R == 4) {
-                const C w1 = tw_dir<DIR>(__ldg(tw + t));
-                const C w2 = tw_dir<DIR>(__ldg(tw + 2 * t));
+                const C w2 = cmul(w1, w1);
                 v[m + 1 * G] = cmul(v[m + 1 * G], w1);
                 v[m + 2 * G] = cmul(v[m + 2 * G], w2);
                 v[m + 3 * G] = cmul(v[m + 3 * G], cmul(w1, w2));
             } else {
-                const C w1 = tw_dir<DIR>(__ldg(tw + t));
                 v[m + 1 * G] = cmul(v[m + 1 * G], w1);
             }
         }
@@ -145,15 +172,27 @@ __device__ __forceinline__ void fft_stage(cx_t<T> (&v)[8], const Lay& lay, const
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = lay.ld(j + q * TPL);
-        fft_stage<T, N, DIR, Ns * R, Lay>(v, lay, j, tw);
+        fft_stage<T, N, DIR, Ns * R, OFF + (Ns > 1 ? G : 0), Lay>(v, lay, j, wr);
     }
 }
 
-// Full transform of the line owned by this thread group.  Unnormalised in both directions.
+// number of twiddle registers (complex) a thread keeps for length N
+template <int N> struct TwN { static constexpr int value = tw_count<N>() > 0 ? tw_count<N>() : 1; };
+
+// Full transform of the line owned by this thread group, twiddles already in registers.  Unnormalised.
+template <typename T, int N, int DIR, typename Lay>
+__device__ __forceinline__ void fft_line(cx_t<T> (&v)[8], const Lay& lay, const int j,
+                                         const cx_t<T> (&wr)[TwN<N>::value]) {
+    fft_stage<T, N, DIR, 1, 0, Lay>(v, lay, j, wr);
+}
+
+// Convenience for kernels that run a single transform: fetch the twiddles, then transform.
 template <typename T, int N, int DIR, typename Lay>
 __device__ __forceinline__ void fft_line(cx_t<T> (&v)[8], const Lay& lay, const int j,
                                          const cx_t<T>* __restrict__ tw) {
-    fft_stage<T, N, DIR, 1, Lay>(v, lay, j, tw);
+    cx_t<T> wr[TwN<N>::value];
+    fft_twiddles<T, N>(wr, j, tw);
+    fft_stage<T, N, DIR, 1, 0, Lay>(v, lay, j, wr);
 }
 
 }  // namespace scb

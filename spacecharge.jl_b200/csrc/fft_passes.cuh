@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
     };
 
     prefetch_S(0);
+    C wr[TwN<N>::value];
+    fft_twiddles<T, N>(wr, j, p.tw);
     C spec[8];
     {
         const C* src = p.in + (long long)kyl * p.PX + kx;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
             spec[q] = (valid && pos < p.nz) ? ld_stream(src + pos * plane) : cmake<C>(0, 0);
         }
     }
-    fft_line<T, N, -1>(spec, lay, j, p.tw);
+    fft_line<T, N, -1>(spec, lay, j, wr);
 
     if constexpr (KIND == GREEN_CATHODE) {
 #pragma unroll
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
             w[q] = acc;
         }
         if (c + 1 < p.ncomp) prefetch_S(c + 1);  // own slots only: no barrier needed before they are overwritten
-        fft_line<T, N, +1>(w, lay, j, p.tw);
+        fft_line<T, N, +1>(w, lay, j, wr);
         const long long dst_off = c * p.out_scomp + (long long)kyl * p.PX + kx;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -381,6 +383,8 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
         if (p.ncomp > 1) load_S(1);
     }
 
+    C wr[TwN<N>::value];
+    fft_twiddles<T, N>(wr, j, p.tw);   // in flight while the input tile travels
     C spec[8];
     mbar_wait(bars + 0, 0);
 #pragma unroll
@@ -388,7 +392,7 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
         const int pos = j + q * TPL;
         spec[q] = (q < 4 && pos < p.nz) ? tile(0)[pos * TX + tx] : cmake<C>(0, 0);
     }
-    fft_line<T, N, -1>(spec, lay, j, p.tw);
+    fft_line<T, N, -1>(spec, lay, j, wr);
 
 #pragma unroll 1
     for (int c = 0; c < p.ncomp; ++c) {
@@ -404,7 +408,7 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
             // field: (a + ib) * (i s) = s * (-b + i a);  potential: (a + ib) * s
             w[q] = c == 3 ? cmake<C>(spec[q].x * s, spec[q].y * s) : cmake<C>(-spec[q].y * s, spec[q].x * s);
         }
-        fft_line<T, N, +1>(w, lay, j, p.tw);
+        fft_line<T, N, +1>(w, lay, j, wr);
         // staging buffer c&1 was handed to the store of component c-2 (c = 0 reuses the input tile, which every thread
         // finished reading before the first barrier of the forward transform)
         if (c >= 2 && leader) bulk_wait_read<1>();
