@@ -208,6 +208,53 @@ end
            half * x^2 * atan(y * z / (x * r)) + y * z * log(x + r) + x * z * log(y + r) + x * y * log(z + r)
 end
 
+# ---- extensions (not in the reference): potential, magnetic field, fused kick -------------------
+"""
+    solve_potential!(mesh; at_cathode=false) -> phi::CuArray{T,3}
+
+`solve!` that also returns the scalar potential (rest-frame, `potential_green_function` as a fourth
+component of the same fused convolution; scb_solve_potential).  `mesh.efield` is written as by `solve!`.
+"""
+function solve_potential!(mesh::Mesh3D{T}; at_cathode::Bool = false) where {T}
+    phi = similar(mesh.rho)
+    h = handle(mesh)
+    check(h, ccall((:scb_solve_potential, LIB), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Float64}, Float64, Cint),
+                   h.ptr, mesh.rho, mesh.efield, phi, dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.max_bounds),
+                   _f3(mesh.delta), Float64(mesh.gamma), at_cathode ? 1 : 0))
+    return phi
+end
+
+"""
+    magnetic_field(mesh) -> B::CuArray{T,4}
+
+B = (beta/c) z_hat x E of a bunch moving along +z with `mesh.gamma` (scb_bfield).
+"""
+function magnetic_field(mesh::Mesh3D{T}) where {T}
+    b = similar(mesh.efield)
+    h = handle(mesh)
+    check(h, ccall((:scb_bfield, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Int64}, Float64),
+                   h.ptr, mesh.efield, b, dtag(T), _n(mesh), Float64(mesh.gamma)))
+    return b
+end
+
+"""
+    interpolate_kick!(mesh, x, y, z, px, py, pz, coef_xy, coef_z)
+
+`interpolate_field` fused with the momentum update `p .+= coef .* E` (scb_interpolate_kick): the
+interpolated field never round-trips through memory.
+"""
+function interpolate_kick!(mesh::Mesh3D{T}, x, y, z, px, py, pz, coef_xy::Real, coef_z::Real) where {T}
+    P = eltype(x)
+    h = handle(mesh)
+    check(h, ccall((:scb_interpolate_kick, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Cint, Ptr{Int64},
+                    Ptr{Float64}, Ptr{Float64}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64),
+                   h.ptr, length(x), x, y, z, dtag(P), mesh.efield, dtag(T), _n(mesh), _f3(mesh.min_bounds),
+                   _f3(mesh.delta), px, py, pz, Float64(coef_xy), Float64(coef_z)))
+end
+
 """
     step!(mesh, x, y, z, q, Ex, Ey, Ez; at_cathode=false)
 
