@@ -759,6 +759,8 @@ int solve_dispatch(scb_handle* h, const void* rho, void* efield, int mdt, const 
 
 Geom3 make_geom(const int64_t n[3], const double lo[3], const double delta[3]) {
     Geom3 g;
+    static const int keep = [] { const char* e = std::getenv("SCB_L2_HINT"); return e ? std::atoi(e) : 1; }();
+    g.l2_keep = keep;
     for (int a = 0; a < 3; ++a) {
         g.n[a] = (int)n[a];
         g.lo[a] = lo[a];

@@ -21,6 +21,7 @@ struct Geom3 {
     double lo[3];
     double delta[3];
     int n[3];
+    int l2_keep = 1;   // 1: grid-side accesses of the particle passes carry an L2 evict_last policy (SCB_L2_HINT=0 disables)
 };
 
 // fused momentum kick of the gather kernels: off = plain interpolate_field (outputs overwritten)

@@ -17,6 +17,24 @@ namespace scb {
 template <typename P, typename T> struct promote { using type = double; };
 template <> struct promote<float, float> { using type = float; };
 
+// L2 residency policy for the grid-side accesses.  The particle streams (3.2 GB in, 2.4 GB out per pass) are
+// read/written once with evict-first loads/stores, but they still wash the scattered grid records out of the
+// 126 MB L2: ncu showed only 70 % of the gather's sector reads and 42 % of the deposit's L2 look-ups hitting although
+// the +-3 sigma core that 99 % of the particles touch is < 100 MB.  Grid records / accumulator tiles are therefore
+// accessed with an evict_last policy so that the streams are evicted in preference to them.
+__device__ __forceinline__ unsigned long long l2_policy(int keep) {
+    unsigned long long p;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_add_hint(double* a, double v, unsigned long long pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_hint(float* a, float v, unsigned long long pol) {
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+
 template <typename W> struct CellW {
     int i[3];
     W f[3];
@@ -138,14 +156,25 @@ __global__ void __launch_bounds__(256) k_deposit_tiles(long long np, const P* __
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
     const int k = lane & 3, kx = k & 1, ky = k >> 1;
+    const unsigned long long pol = l2_policy(g.l2_keep);
+    // next group's particle data requested one iteration ahead (the reductions are fire-and-forget, so the loads of
+    // x, y, z, q are the only latency on the critical path)
+    P px = 0, py = 0, pz = 0, pq = 0;
+    if (warp * 32 + lane < np) {
+        const long long i0 = warp * 32 + lane;
+        px = ld_stream(x + i0); py = ld_stream(y + i0); pz = ld_stream(z + i0); pq = ld_stream(q + i0);
+    }
     for (long long base = warp * 32; base < np; base += nwarps * 32) {
         const long long i = base + lane;
+        const long long inext = i + nwarps * 32;
+        P nx_ = 0, ny_ = 0, nz_ = 0, nq_ = 0;
+        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); nq_ = ld_stream(q + inext); }
         W f0 = 0, f1 = 0, f2 = 0, charge = 0;
         long long off = 0;
         if (i < np) {
             CellW<W> c;
-            locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
-            charge = (W)ld_stream(q + i);
+            locate<W>((W)px, (W)py, (W)pz, g, c);
+            charge = (W)pq;
             f0 = c.f[0]; f1 = c.f[1]; f2 = c.f[2];
             off = c.i[0] + sy * c.i[1] + sz * c.i[2];
         }
@@ -161,10 +190,11 @@ __global__ void __launch_bounds__(256) k_deposit_tiles(long long np, const P* __
                 const W one = (W)1;
                 const W qxy = qq * (kx ? fx : one - fx) * (ky ? fy : one - fy);   // (charge * w_x) * w_y
                 T* t = tiles + 4 * o + k;
-                atomicAdd(t, (T)(qxy * (one - fz)));
-                atomicAdd(t + 4 * sz, (T)(qxy * fz));
+                red_add_hint(t, (T)(qxy * (one - fz)), pol);
+                red_add_hint(t + 4 * sz, (T)(qxy * fz), pol);
             }
         }
+        px = nx_; py = ny_; pz = nz_; pq = nq_;
     }
 }
 
@@ -255,13 +285,14 @@ __global__ void __launch_bounds__(256) k_pack_efield_f32(const float* __restrict
     out[2 * i + 1] = b;
 }
 
-__device__ __forceinline__ void ld256(const double4* p, double (&v)[4]) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+__device__ __forceinline__ void ld256(const double4* p, double (&v)[4], unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p), "l"(pol));
 }
-__device__ __forceinline__ void ld256(const float4* p, float (&v)[8]) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+__device__ __forceinline__ void ld256(const float4* p, float (&v)[8], unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
 }
 
 template <typename P>
@@ -273,19 +304,20 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f64(long long np, co
     using W = double;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const unsigned long long pol = l2_policy(g.l2_keep);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
         CellW<W> c;
         locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
         const double4* b = e + c.i[0] + sy * c.i[1] + sz * c.i[2];
         double n000[4], n100[4], n010[4], n110[4], n001[4], n101[4], n011[4], n111[4];
-        ld256(b, n000);
-        ld256(b + 1, n100);
-        ld256(b + sy, n010);
-        ld256(b + sy + 1, n110);
-        ld256(b + sz, n001);
-        ld256(b + sz + 1, n101);
-        ld256(b + sz + sy, n011);
-        ld256(b + sz + sy + 1, n111);
+        ld256(b, n000, pol);
+        ld256(b + 1, n100, pol);
+        ld256(b + sy, n010, pol);
+        ld256(b + sy + 1, n110, pol);
+        ld256(b + sz, n001, pol);
+        ld256(b + sz + 1, n101, pol);
+        ld256(b + sz + sy, n011, pol);
+        ld256(b + sz + sy + 1, n111, pol);
         const W dx = c.f[0], dy = c.f[1], dz = c.f[2], one = 1.0;
         const W w000 = (one - dx) * (one - dy) * (one - dz);
         const W w100 = dx * (one - dy) * (one - dz);
@@ -325,6 +357,7 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const unsigned long long pol = l2_policy(g.l2_keep);
     const int kx = lane & 1;
     for (long long base = warp * 32; base < np; base += nwarps * 32) {
         const long long i = base + lane;
@@ -346,10 +379,10 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
             const long long o = __shfl_sync(FULL, off, src);
             const double4* b = e + o + kx;
             double n00[4], n10[4], n01[4], n11[4];   // (y,z), (y+1,z), (y,z+1), (y+1,z+1) at this lane's x corner
-            ld256(b, n00);
-            ld256(b + sy, n10);
-            ld256(b + sz, n01);
-            ld256(b + sz + sy, n11);
+            ld256(b, n00, pol);
+            ld256(b + sy, n10, pol);
+            ld256(b + sz, n01, pol);
+            ld256(b + sz + sy, n11, pol);
             const W one = 1.0;
             const W wx = kx ? dx : one - dx;
             const W w00 = wx * (one - dy) * (one - dz);
@@ -374,6 +407,71 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
     }
 }
 
+// Lane pairs without broadcast / compaction shuffles.  The LSU data pipe is the busiest unit of the kernel above
+// (ncu: 81 % of its wavefront rate) and shuffles travel through the same pipe: per 32 particles it spent 44
+// wavefronts on shuffles (coordinates and offset broadcast to the pair, results gathered back for a coalesced
+// store) next to ~144 on the gathers themselves.  Here both lanes of a pair load the particle's coordinates
+// themselves (same address: one wavefront per 16 particles and array), locate it redundantly, and the even lane
+// stores the result (16 active lanes, one 128-byte line): 12 shuffle wavefronts per 32 particles remain (the x0 + x1
+// halves of the three components).  Same arithmetic, bit-identical results.
+template <typename P>
+__global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
+                                                                const P* __restrict__ y, const P* __restrict__ z,
+                                                                const double4* __restrict__ e, const Geom3 g,
+                                                                P* __restrict__ ex, P* __restrict__ ey,
+                                                                P* __restrict__ ez, const Kick kick) {
+    using W = double;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+    const unsigned long long pol = l2_policy(g.l2_keep);
+    const int kx = lane & 1;
+    // the coordinates of the next group are requested before the gathers of the current one are consumed: the kernel is
+    // latency-bound (ncu: long-scoreboard stalls 12 per issued instruction), and this takes the DRAM round trip of the
+    // particle stream off the critical path of every iteration
+    long long i = warp * 16 + (lane >> 1);
+    P cx = 0, cy = 0, cz = 0;
+    if (i < np) { cx = ld_stream(x + i); cy = ld_stream(y + i); cz = ld_stream(z + i); }
+    for (; __any_sync(FULL, i < np); i += nwarps * 16) {
+        const bool live = i < np;
+        const long long inext = i + nwarps * 16;
+        P nx_ = 0, ny_ = 0, nz_ = 0;
+        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); }
+        W acc[3] = {0, 0, 0};
+        if (live) {
+            CellW<W> c;
+            locate<W>((W)cx, (W)cy, (W)cz, g, c);
+            const double4* b = e + (c.i[0] + sy * c.i[1] + sz * c.i[2]) + kx;
+            double n00[4], n10[4], n01[4], n11[4];   // (y,z), (y+1,z), (y,z+1), (y+1,z+1) at this lane's x corner
+            ld256(b, n00, pol);
+            ld256(b + sy, n10, pol);
+            ld256(b + sz, n01, pol);
+            ld256(b + sz + sy, n11, pol);
+            const W dx = c.f[0], dy = c.f[1], dz = c.f[2], one = 1.0;
+            const W wx = kx ? dx : one - dx;
+            const W w00 = wx * (one - dy) * (one - dz);
+            const W w10 = wx * dy * (one - dz);
+            const W w01 = wx * (one - dy) * dz;
+            const W w11 = wx * dy * dz;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] = n00[k] * w00 + n10[k] * w10 + n01[k] * w01 + n11[k] * w11;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const W other = __shfl_xor_sync(FULL, acc[k], 1);
+            acc[k] = kx ? other + acc[k] : acc[k] + other;   // x0 part + x1 part
+        }
+        if (live && kx == 0) {
+            put_result<P, W>(ex, i, acc[0], kick, false);
+            put_result<P, W>(ey, i, acc[1], kick, false);
+            put_result<P, W>(ez, i, acc[2], kick, true);
+        }
+        cx = nx_; cy = ny_; cz = nz_;
+    }
+}
+
 template <typename P>
 __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, const P* __restrict__ x,
                                                                  const P* __restrict__ y, const P* __restrict__ z,
@@ -383,15 +481,23 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
     using W = typename promote<P, float>::type;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
+    const unsigned long long pol = l2_policy(g.l2_keep);
+    // coordinates requested one iteration ahead (latency-bound gather, see k_interpolate_pair2_f64)
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    P cx = 0, cy = 0, cz = 0;
+    if (i < np) { cx = ld_stream(x + i); cy = ld_stream(y + i); cz = ld_stream(z + i); }
+    for (; i < np; i += stride) {
+        const long long inext = i + stride;
+        P nx_ = 0, ny_ = 0, nz_ = 0;
+        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); }
         CellW<W> c;
-        locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+        locate<W>((W)cx, (W)cy, (W)cz, g, c);
         const float4* b = e + 2 * (c.i[0] + sy * c.i[1] + sz * c.i[2]);
         float p00[8], p10[8], p01[8], p11[8];  // x-pairs at (y,z), (y+1,z), (y,z+1), (y+1,z+1)
-        ld256(b, p00);
-        ld256(b + 2 * sy, p10);
-        ld256(b + 2 * sz, p01);
-        ld256(b + 2 * (sz + sy), p11);
+        ld256(b, p00, pol);
+        ld256(b + 2 * sy, p10, pol);
+        ld256(b + 2 * sz, p01, pol);
+        ld256(b + 2 * (sz + sy), p11, pol);
         const W dx = c.f[0], dy = c.f[1], dz = c.f[2], one = (W)1;
         const W w000 = (one - dx) * (one - dy) * (one - dz);
         const W w100 = dx * (one - dy) * (one - dz);
@@ -409,6 +515,7 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
         put_result<P, W>(ex, i, out[0], kick, false);
         put_result<P, W>(ey, i, out[1], kick, false);
         put_result<P, W>(ez, i, out[2], kick, true);
+        cx = nx_; cy = ny_; cz = nz_;
     }
 }
 
@@ -560,6 +667,9 @@ cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void
     if (mdt == 1 && thread_per_particle) {
         if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
+    } else if (mdt == 1 && imode != 3) {
+        if (pdt == 1) k_interpolate_pair2_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
+        else k_interpolate_pair2_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else if (mdt == 1) {
         if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
