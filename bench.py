@@ -321,7 +321,7 @@ def main():
         gbs = ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0
         stage_roof[k] = {"ms": round(stage[k], 4), "alg_MB": round(ab[k] / 1e6, 1), "GBps": round(gbs, 1),
                          "frac": round(gbs / peak, 4)}
-    kernel_names = {"deposit": "k_deposit_tiles", "interpolate": "k_interpolate_pair_f64" if s == 8 else "k_interpolate_packed_f32",
+    kernel_names = {"deposit": "k_deposit_tiles", "interpolate": "k_interpolate_pair2_f64" if s == 8 else "k_interpolate_packed_f32",
                     "F1": "k_x_r2c", "F2": "k_lines<-1>",
                     "Z": "k_z_tma" if (world == 1 and not at_cathode and grid[2] <= 256) else "k_z_fused",
                     "B2": "k_lines<+1>", "B3": "k_x_c2r"}

@@ -324,8 +324,13 @@ class Mesh3D:
         re-allocating rho / efield.  The extrema come from one fused device reduction (scb_bounds); the
         next solve_ rebuilds the Green spectrum for the new spacing (cold-geometry path)."""
         npdt = np.dtype(self.T).type
+        old = (self.min_bounds, self.max_bounds, self.delta)
         self.min_bounds, self.max_bounds, self.delta = self._auto_bounds(
             self.grid_size, particles_x, particles_y, particles_z, npdt, self.device, self.handle, self.group)
+        if (self.min_bounds, self.max_bounds, self.delta) != old:
+            # a tracking loop never returns to an old spacing: hand the old spectrum's buffer back to the
+            # handle's pool so that the rebuild reuses it (no cudaMalloc / cudaFree in steady state)
+            self.handle.drop_green_cache()
         return self
 
     def reduce_rho_(self):

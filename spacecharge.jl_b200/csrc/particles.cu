@@ -560,10 +560,25 @@ __global__ void __launch_bounds__(256) k_bounds(long long np, const P* __restric
                                                  const P* __restrict__ z, unsigned long long* __restrict__ out6) {
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
-        const double p[3] = {(double)x[i], (double)y[i], (double)z[i]};
+    const P* arr[3] = {x, y, z};
+    // four independent streaming loads per array and iteration keep enough bytes in flight for HBM
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < np; i += 4 * stride) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], p[a]); hi[a] = fmax(hi[a], p[a]); }
+        for (int a = 0; a < 3; ++a) {
+            const double v0 = (double)ld_stream(arr[a] + i), v1 = (double)ld_stream(arr[a] + i + stride);
+            const double v2 = (double)ld_stream(arr[a] + i + 2 * stride), v3 = (double)ld_stream(arr[a] + i + 3 * stride);
+            lo[a] = fmin(fmin(lo[a], fmin(v0, v1)), fmin(v2, v3));
+            hi[a] = fmax(fmax(hi[a], fmax(v0, v1)), fmax(v2, v3));
+        }
+    }
+    for (; i < np; i += stride) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double v = (double)ld_stream(arr[a] + i);
+            lo[a] = fmin(lo[a], v);
+            hi[a] = fmax(hi[a], v);
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -702,7 +717,7 @@ cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, c
     unsigned long long* o = reinterpret_cast<unsigned long long*>(out6);
     k_bounds_init<<<1, 32, 0, s>>>(o);
     if (np > 0) {
-        const unsigned grid = particle_grid(np, 256, 8);
+        const unsigned grid = particle_grid(np, 256, 16);
         if (pdt == 0) k_bounds<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, o);
         else k_bounds<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, o);
     }
