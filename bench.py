@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stages-only", action="store_true", help="print only the per-stage device times (tuning)")
     ap.add_argument("--replicated-solve", action="store_true", help="multi-GPU: all-reduce rho and solve on every rank")
+    ap.add_argument("--sharded-solve", action="store_true", help="multi-GPU: force the slab-decomposed solve (default: from 4 GPUs on)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-structure-on-GPU baseline")
     args = ap.parse_args()
 
@@ -229,7 +230,7 @@ def main():
     ex, ey, ez = (torch.empty_like(x) for _ in range(3))
 
     mesh = scb.Mesh3D(grid, x, y, z, T=npdt, total_charge=QTOT, group=group,
-                      sharded_solve=not args.replicated_solve)   # built once, outside the timed region
+                      sharded_solve=False if args.replicated_solve else (True if args.sharded_solve else None))   # built once, outside the timed region
     if world > 1 and not mesh.sharded:
         config["parallelism"] = "particles sharded over %d GPUs, rho all-reduced (NCCL), solve replicated" % world
     hd = mesh.handle
@@ -337,18 +338,32 @@ def main():
     e2e = None
     if not args.no_e2e and world == 1:
         hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
-        hex_, hey, hez = (torch.empty_like(hx).pin_memory() for _ in range(3))
+        houts = [[torch.empty_like(hx).pin_memory() for _ in range(3)] for _ in range(2)]
         for _ in range(2):
-            scb.step_host_(mesh, hx, hy, hz, hq, hex_, hey, hez, at_cathode=at_cathode)
-        ksteps = max(1, min(args.steps, 5))
+            scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)
+        ksteps = max(2, min(args.steps, 6))
+        # (a) blocking call: one bunch at a time, upload -> step -> download
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            scb.step_host_(mesh, hx, hy, hz, hq, hex_, hey, hez, at_cathode=at_cathode)   # synchronous on return
+            scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)   # synchronous on return
+        t_sync = (time.perf_counter() - t0) / ksteps
+        # (b) bunches queued back to back (scb_step_host_async): every step still uploads its own inputs and downloads
+        # its own results, but the upload of step k+1 overlaps the download of step k (two staging slots)
+        for k in range(2):
+            scb.step_host_async_(mesh, hx, hy, hz, hq, *houts[k & 1], at_cathode=at_cathode)
+        scb.step_host_wait_(mesh)
+        t0 = time.perf_counter()
+        for k in range(ksteps):
+            scb.step_host_async_(mesh, hx, hy, hz, hq, *houts[k & 1], at_cathode=at_cathode)
+        scb.step_host_wait_(mesh)
         t_e2e = (time.perf_counter() - t0) / ksteps
         e2e = {"value": npart / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": 4 * n_local * s,
                "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * t_e2e, "steps": ksteps,
-               "api": "scb_step_host (pinned host particle arrays in, pinned host E arrays out)"}
+               "api": "scb_step_host_async x steps + scb_step_host_wait (pinned host particle arrays in, pinned host E "
+                      "arrays out; consecutive steps overlap upload and download over the full-duplex link)",
+               "blocking_call": {"api": "scb_step_host", "ms_per_step": 1e3 * t_sync, "value": npart / t_sync}}
+        del houts
     elif not args.no_e2e:
         # sharded: every rank feeds its own shard from pinned host memory
         hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))

@@ -168,6 +168,20 @@ SCB_API int scb_step_host(scb_handle* h, int64_t np, const void* x_host, const v
                   const double max_bounds[3], const double delta[3], double gamma,
                   int at_cathode, void* ex_host, void* ey_host, void* ez_host);
 
+/* Stream-pipelined form of scb_step_host for callers that push several independent bunches (or
+ * repeat the step on fresh host data): returns as soon as the copies and kernels are queued.  Up to
+ * two steps may be in flight -- they alternate between two device staging slots, so the host->device
+ * copy of step k+1 runs while the device->host copy of step k is still draining (PCIe is full
+ * duplex).  The host buffers of a step (inputs and outputs) must stay untouched, and the output
+ * buffers of two consecutive steps must be distinct, until scb_step_host_wait returns.  rho/efield
+ * hold the grids of the most recently queued step. */
+SCB_API int scb_step_host_async(scb_handle* h, int64_t np, const void* x_host, const void* y_host,
+                  const void* z_host, const void* q_host, int pdt, void* rho, void* efield,
+                  int mdt, const int64_t n[3], const double min_bounds[3],
+                  const double max_bounds[3], const double delta[3], double gamma,
+                  int at_cathode, void* ex_host, void* ey_host, void* ez_host);
+SCB_API int scb_step_host_wait(scb_handle* h);
+
 /* ---- multi-GPU: particle-sharded step with a slab-decomposed solve (NCCL over NVLink) ------- */
 /* One process and one handle per GPU.  scb_comm_unique_id fills 128 bytes on one rank; the caller
  * broadcasts them (torch.distributed / MPI) and every rank calls scb_comm_init.  NCCL is dlopen'ed

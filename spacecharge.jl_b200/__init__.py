@@ -22,7 +22,7 @@ from . import _lib
 from ._lib import LibraryMissing, ScbError  # noqa: F401
 
 __all__ = ["Mesh3D", "deposit_", "clear_mesh_", "interpolate_field", "solve_", "solve_freespace_",
-           "get_green_function_", "cell_indices", "step_", "step_host_", "ErrorException", "CLIGHT", "FPEI",
+           "get_green_function_", "cell_indices", "step_", "step_host_", "step_host_async_", "step_host_wait_", "ErrorException", "CLIGHT", "FPEI",
            "solve_potential_", "magnetic_field", "interpolate_kick_",
            "Handle", "default_handle"]
 
@@ -195,7 +195,7 @@ class Mesh3D:
 
     def __init__(self, grid_size: Sequence[int], *args, T=np.float64, gamma: float = 1.0,
                  total_charge: float = 0.0, device: Optional[int] = None, handle: Optional[Handle] = None,
-                 group=None, sharded_solve: bool = True):
+                 group=None, sharded_solve: Optional[bool] = None):
         torch = _torch()
         grid_size = tuple(int(g) for g in grid_size)
         if len(grid_size) != 3:
@@ -237,7 +237,13 @@ class Mesh3D:
         # slab-decomposed solve (scb_solve_sharded) when the grid divides over the ranks; otherwise
         # rho is all-reduced and the solve replicated.  In the sharded mode mesh.rho holds this
         # rank's PARTIAL charge grid after deposit_ (call reduce_rho_() to materialise the sum).
+        # sharded_solve=None picks by rank count: on two GPUs the replicated solve is faster (measured, config 5:
+        # 4.76 ms against 4.99 ms per step -- half of the three-component spectrum crosses NVLink in the transposes),
+        # from four GPUs on the slab-decomposed solve wins (8 GPUs: 2.45 ms against 4.15 ms).
         self.sharded = False
+        if group is not None and sharded_solve is None:
+            import torch.distributed as dist
+            sharded_solve = dist.get_world_size(group) >= 4
         if group is not None and sharded_solve:
             import torch.distributed as dist
             w = dist.get_world_size(group)
@@ -510,22 +516,39 @@ def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> Non
                                     ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
 
 
+def _host_ptr(a):
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == "cpu" and a.is_contiguous()
+        return a.data_ptr(), a.dtype
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data, (torch.float32 if a.dtype == np.float32 else torch.float64)
+
+
+def _step_host(fn_name, mesh, x, y, z, q, ex, ey, ez, at_cathode):
+    hd = mesh.handle
+    hd.use_current_stream()
+    (px, dt), (py, _), (pz, _), (pq, _) = (_host_ptr(a) for a in (x, y, z, q))
+    (pex, _), (pey, _), (pez, _) = (_host_ptr(a) for a in (ex, ey, ez))
+    hd.check(getattr(hd.lib, fn_name)(hd.h, len(x), px, py, pz, pq, _tag(dt), mesh._rho.data_ptr(),
+                                      mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(),
+                                      float(mesh.gamma), 1 if at_cathode else 0, pex, pey, pez))
+
+
 def step_host_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
     """The same step with HOST particle buffers (numpy arrays or CPU torch tensors, ideally
     pinned): host->device and device->host copies are part of the call (scb_step_host)."""
-    torch = _torch()
+    _step_host("scb_step_host", mesh, x, y, z, q, ex, ey, ez, at_cathode)
+
+
+def step_host_async_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
+    """Queue a host-buffer step and return (scb_step_host_async).  Up to two steps may be in flight: the
+    upload of one overlaps the download of the previous one.  The output buffers of consecutive steps
+    must be distinct and every buffer must stay alive and untouched until step_host_wait_."""
+    _step_host("scb_step_host_async", mesh, x, y, z, q, ex, ey, ez, at_cathode)
+
+
+def step_host_wait_(mesh: Mesh3D) -> None:
+    """Wait for every queued host-buffer step (scb_step_host_wait)."""
     hd = mesh.handle
-    hd.use_current_stream()
-
-    def ptr(a):
-        if isinstance(a, torch.Tensor):
-            assert a.device.type == "cpu" and a.is_contiguous()
-            return a.data_ptr(), a.dtype
-        assert a.flags["C_CONTIGUOUS"]
-        return a.ctypes.data, (torch.float32 if a.dtype == np.float32 else torch.float64)
-
-    (px, dt), (py, _), (pz, _), (pq, _) = ptr(x), ptr(y), ptr(z), ptr(q)
-    (pex, _), (pey, _), (pez, _) = ptr(ex), ptr(ey), ptr(ez)
-    hd.check(hd.lib.scb_step_host(hd.h, len(x), px, py, pz, pq, _tag(dt), mesh._rho.data_ptr(), mesh._efield.data_ptr(),
-                                  mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma),
-                                  1 if at_cathode else 0, pex, pey, pez))
+    hd.check(hd.lib.scb_step_host_wait(hd.h))

@@ -86,10 +86,16 @@ struct scb_handle {
     unsigned long long arena_gen = 0, peer_gen = ~0ull;
     std::vector<void*> peer_arena;
     char* d_ipc = nullptr;         // nranks * 64 bytes of IPC handles + 2 ints (flag, barrier)
-    cudaStream_t copy_stream = nullptr;
-    void* stage = nullptr;
-    size_t stage_bytes = 0;
-    std::vector<cudaEvent_t> chunk_ev;
+    // host-buffer steps: two staging slots so that the upload of step k+1 overlaps the download of step k
+    cudaStream_t copy_stream = nullptr;   // host -> device
+    cudaStream_t d2h_stream = nullptr;    // device -> host
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    std::vector<cudaEvent_t> chunk_ev[2];
+    cudaEvent_t slot_in_free[2] = {nullptr, nullptr};    // compute stream: last kernel that reads the slot's x,y,z,q
+    cudaEvent_t slot_out_free[2] = {nullptr, nullptr};   // d2h stream: last copy that reads the slot's ex,ey,ez
+    bool slot_used[2] = {false, false};
+    int host_steps_in_flight = 0;
 };
 
 namespace {
@@ -309,6 +315,12 @@ Plan make_plan(const int64_t n[3]) {
 }
 
 // ---- Green spectrum: build (cold) and cache ------------------------------------------------
+// SCB_GREEN_REAL=0 selects the complex passes + compress kernel for the free-space build (A/B timing, debugging)
+bool real_sym_disabled() {
+    static const bool off = [] { const char* e = getenv("SCB_GREEN_REAL"); return e && e[0] == '0'; }();
+    return off;
+}
+
 int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& ent, int ncomp) {
     IgfGeom g{};
     for (int a = 0; a < 3; ++a) {
@@ -390,6 +402,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     const bool foldZ = g.sym[2] && !g.corr[2];
     const int rowsY = foldY ? Lyh1 : pl.L[1];
     const int rowsZ = foldZ ? Lzh1 : pl.L[2];
+    const bool real_sym = key.kind == 0 && g.sym[0] && g.sym[1] && g.sym[2] && !real_sym_disabled();
     for (int c = 0; c < ncomp; ++c) {
         // components 0..2 = reference icomp 1..3 (src/green_functions.jl:90-98); component 3 = potential (icomp 0)
         const int icomp = c < 3 ? c + 1 : 0;
@@ -413,6 +426,51 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         xp.n_real = pl.L[0];
         xp.PX = pl.PX;
         xp.scale = 1.0;
+        char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
+        if (real_sym) {
+            // Free space: the padded IGF is real and even / odd about 0 along every axis, so the spectrum stays
+            // "real up to a power of i" through all three passes.  The x pass stores only that real part; the y and
+            // z passes then see PAIRS of adjacent kx lines as one complex line (a + i b): half the lines, half the
+            // bytes, and the last pass writes the cached real spectrum S directly (Float64) -- no compress kernel.
+            const int PXc = pl.PX / 2;
+            xp.real_out = (c == 0) ? 2 : 1;                  // odd along x only for E_x
+            SCB_CUDA(h, launch_x_r2c<double>(pl.L[0], xp, 1, h->stream));
+            LinesParams<double> yp{};
+            yp.in = spec;                                    // pairs [kx/2][Y < rowsY][Z < rowsZ]
+            yp.out = Y2;                                     // pairs [kx/2][ky < Lyh1][Z < rowsZ]
+            yp.tw = twy;
+            yp.n_in = pl.L[1];
+            yp.n_out = Lyh1;
+            yp.ninner = PXc;
+            yp.in_sline = yp.out_sline = PXc;
+            yp.in_souter = (long long)PXc * rowsY;
+            yp.out_souter = (long long)PXc * Lyh1;
+            yp.in_fold = 1;
+            yp.fold_sign = (c == 1) ? -1.0 : 1.0;
+            yp.out_rot = (c == 1) ? 1 : 0;
+            yp.scale = 1.0;
+            SCB_CUDA(h, launch_lines<double>(pl.L[1], -1, yp, rowsZ, 1, h->stream));
+            LinesParams<double> zp{};
+            zp.in = Y2;
+            zp.out = f64 ? reinterpret_cast<double2*>(dst) : spec;   // pairs [kx/2][ky < Lyh1][kz < Lzh1]
+            zp.tw = twz;
+            zp.n_in = pl.L[2];
+            zp.n_out = Lzh1;
+            zp.ninner = PXc;
+            zp.in_sline = zp.out_sline = (long long)PXc * Lyh1;
+            zp.in_souter = zp.out_souter = PXc;
+            zp.in_fold = 1;
+            zp.fold_sign = (c == 2) ? -1.0 : 1.0;
+            zp.out_rot = (c == 2) ? 1 : 0;
+            zp.scale = 1.0;
+            SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, Lyh1, 1, h->stream));
+            h->launches += 5;
+            if (!f64) {
+                SCB_CUDA(h, launch_green_real_to_f32(dst, reinterpret_cast<const double*>(spec), (long long)per_comp, h->stream));
+                h->launches += 1;
+            }
+            continue;
+        }
         SCB_CUDA(h, launch_x_r2c<double>(pl.L[0], xp, 1, h->stream));
         const int ly_out = prune ? Lyh1 : pl.L[1];   // ky kept after the y pass
         const int lz_out = prune ? Lzh1 : pl.L[2];
@@ -448,7 +506,6 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         zp.scale = 1.0;
         SCB_CUDA(h, launch_lines<double>(pl.L[2], -1, zp, ly_out, 1, h->stream));
         const double2* final_spec = zdst;
-        char* dst = static_cast<char*>(ent.data) + (size_t)c * per_comp * elem;
         if (key.kind == 0)
             SCB_CUDA(h, launch_green_compress_free(dst, f64, final_spec, pl.ninner, pl.PX, Lyh1, Lzh1, icomp == 0, h->stream));
         else
@@ -822,14 +879,16 @@ int scb_destroy(scb_handle* h) {
     if (!h) return SCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->copy_stream) {
-        cudaStreamSynchronize(h->copy_stream);
-        cudaStreamDestroy(h->copy_stream);
-    }
+    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream})
+        if (cs) {
+            cudaStreamSynchronize(cs);
+            cudaStreamDestroy(cs);
+        }
     free_green(h, true);
     for (auto& kv : h->twiddles) cudaFree(kv.second);
     if (h->arena) cudaFree(h->arena);
-    if (h->stage) cudaFree(h->stage);
+    for (void* st : h->stage)
+        if (st) cudaFree(st);
     if (h->packed) cudaFree(h->packed);
     if (h->tiles) cudaFree(h->tiles);
     if (h->slab) cudaFree(h->slab);
@@ -839,7 +898,10 @@ int scb_destroy(scb_handle* h) {
     if (h->d_bounds) cudaFree(h->d_bounds);
     if (h->ev_ready)
         for (auto& e : h->ev) cudaEventDestroy(e);
-    for (auto& e : h->chunk_ev) cudaEventDestroy(e);
+    for (auto& v : h->chunk_ev)
+        for (auto& e : v) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->slot_in_free[0], h->slot_in_free[1], h->slot_out_free[0], h->slot_out_free[1]})
+        if (e) cudaEventDestroy(e);
     delete h;
     return SCB_OK;
 }
@@ -1064,10 +1126,10 @@ int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, const void
     return scb_interpolate(h, np, x, y, z, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
 }
 
-int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
-                  void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
-                  const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
-                  void* eyh, void* ezh) {
+int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
+                        void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                        const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
+                        void* eyh, void* ezh) {
     if (!h) return SCB_ERR_INVALID_ARG;
     if (np <= 0 || !xh || !yh || !zh || !qh || !exh || !eyh || !ezh || !rho || !efield || !valid_dt(pdt) || !valid_dt(mdt))
         return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_step_host");
@@ -1075,43 +1137,53 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
     SCB_CUDA(h, cudaSetDevice(h->device));
     const size_t es = dt_size(pdt);
     const size_t arr = ((size_t)np * es + 255) / 256 * 256;
-    if (h->stage_bytes < 7 * arr) {
-        if (h->stage) {
+    const int slot = h->host_steps_in_flight & 1;
+    if (h->stage_bytes[slot] < 7 * arr) {
+        if (h->stage[slot]) {
             SCB_CUDA(h, cudaDeviceSynchronize());
-            cudaFree(h->stage);
-            h->stage = nullptr;
-            h->stage_bytes = 0;
+            cudaFree(h->stage[slot]);
+            h->stage[slot] = nullptr;
+            h->stage_bytes[slot] = 0;
+            h->slot_used[slot] = false;
         }
-        if (cudaMalloc(&h->stage, 7 * arr) != cudaSuccess) {
+        if (cudaMalloc(&h->stage[slot], 7 * arr) != cudaSuccess) {
             (void)cudaGetLastError();
             return fail(h, SCB_ERR_ALLOC, "particle staging allocation failed");
         }
-        h->stage_bytes = 7 * arr;
+        h->stage_bytes[slot] = 7 * arr;
     }
     if (!h->copy_stream) SCB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->d2h_stream) SCB_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&h->slot_in_free[slot], &h->slot_out_free[slot]})
+        if (!*e) SCB_CUDA(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     char* d[7];
-    for (int i = 0; i < 7; ++i) d[i] = static_cast<char*>(h->stage) + i * arr;
+    for (int i = 0; i < 7; ++i) d[i] = static_cast<char*>(h->stage[slot]) + i * arr;
     const void* src[4] = {xh, yh, zh, qh};
     void* dsth[3] = {exh, eyh, ezh};
 
     const int64_t chunk = 1 << 22;
     const int nchunk = (int)((np + chunk - 1) / chunk);
-    while ((int)h->chunk_ev.size() < 2 * nchunk + 2) {
+    std::vector<cudaEvent_t>& cev = h->chunk_ev[slot];
+    while ((int)cev.size() < 2 * nchunk + 1) {
         cudaEvent_t e;
         SCB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->chunk_ev.push_back(e);
+        cev.push_back(e);
     }
     const Geom3 g = make_geom(n, min_bounds, delta);
-    // make the copy stream wait for whatever the caller queued before this call
-    SCB_CUDA(h, cudaEventRecord(h->chunk_ev[2 * nchunk], h->stream));
-    SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * nchunk], 0));
+    if (h->host_steps_in_flight == 0) {
+        // first step of a pipeline: the upload waits for whatever the caller queued before this call
+        SCB_CUDA(h, cudaEventRecord(cev[2 * nchunk], h->stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, cev[2 * nchunk], 0));
+    }
+    // the slot's inputs were last read by the gather of the step two calls back
+    if (h->slot_used[slot]) SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->slot_in_free[slot], 0));
     SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)n[0] * n[1] * n[2] * dt_size(mdt), h->stream));
     for (int c = 0; c < nchunk; ++c) {
         const int64_t o = (int64_t)c * chunk, m = (np - o) < chunk ? (np - o) : chunk;
         for (int a = 0; a < 4; ++a)
             SCB_CUDA(h, cudaMemcpyAsync(d[a] + o * es, (const char*)src[a] + o * es, m * es, cudaMemcpyHostToDevice, h->copy_stream));
-        SCB_CUDA(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
-        SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+        SCB_CUDA(h, cudaEventRecord(cev[c], h->copy_stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->stream, cev[c], 0));
         SCB_CUDA(h, launch_deposit(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, d[3] + o * es, rho, g, h->opt.deposit_mode, h->stream));
         h->launches += 1;
     }
@@ -1123,6 +1195,8 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
         h->launches += 1;
         packed_ready = true;
     }
+    // the slot's outputs were last read by the download of the step two calls back
+    if (h->slot_used[slot]) SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->slot_out_free[slot], 0));
     for (int c = 0; c < nchunk; ++c) {
         const int64_t o = (int64_t)c * chunk, m = (np - o) < chunk ? (np - o) : chunk;
         if (packed_ready) {
@@ -1133,14 +1207,38 @@ int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, con
                                            d[5] + o * es, d[6] + o * es, h->stream));
         }
         h->launches += 1;
-        SCB_CUDA(h, cudaEventRecord(h->chunk_ev[nchunk + c], h->stream));
-        SCB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[nchunk + c], 0));
+        SCB_CUDA(h, cudaEventRecord(cev[nchunk + c], h->stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, cev[nchunk + c], 0));
         for (int a = 0; a < 3; ++a)
-            SCB_CUDA(h, cudaMemcpyAsync((char*)dsth[a] + o * es, d[4 + a] + o * es, m * es, cudaMemcpyDeviceToHost, h->copy_stream));
+            SCB_CUDA(h, cudaMemcpyAsync((char*)dsth[a] + o * es, d[4 + a] + o * es, m * es, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
-    SCB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
-    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    SCB_CUDA(h, cudaEventRecord(h->slot_in_free[slot], h->stream));
+    SCB_CUDA(h, cudaEventRecord(h->slot_out_free[slot], h->d2h_stream));
+    h->slot_used[slot] = true;
+    h->host_steps_in_flight += 1;
     return SCB_OK;
+}
+
+int scb_step_host_wait(scb_handle* h) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    if (h->copy_stream) SCB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->d2h_stream) SCB_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->host_steps_in_flight = 0;
+    return SCB_OK;
+}
+
+int scb_step_host(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
+                  void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                  const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
+                  void* eyh, void* ezh) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (h->host_steps_in_flight) SCB_TRY(scb_step_host_wait(h));
+    const int rc = scb_step_host_async(h, np, xh, yh, zh, qh, pdt, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma,
+                                       at_cathode, exh, eyh, ezh);
+    const int rw = scb_step_host_wait(h);
+    return rc != SCB_OK ? rc : rw;
 }
 
 int scb_drop_green_cache(scb_handle* h) {
@@ -1151,7 +1249,7 @@ int scb_drop_green_cache(scb_handle* h) {
 
 int64_t scb_workspace_bytes(const scb_handle* h) {
     if (!h) return 0;
-    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes + (int64_t)h->packed_bytes + (int64_t)h->tiles_bytes;
+    int64_t b = (int64_t)h->arena_bytes + (int64_t)h->stage_bytes[0] + (int64_t)h->stage_bytes[1] + (int64_t)h->packed_bytes + (int64_t)h->tiles_bytes;
     for (auto& e : h->green) b += (int64_t)e.cap;
     for (auto& e : h->green_pool) b += (int64_t)e.second;
     return b;

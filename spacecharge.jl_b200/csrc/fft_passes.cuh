@@ -77,6 +77,10 @@ struct LinesParams {
     int in_fold;
     T fold_sign;
     T scale;
+    // Green-spectrum build on real-symmetric data: the complex line is a PAIR of real lines (a + i b).  Both are
+    // even => the output is (A, B) with A, B real.  Both odd => A = i A~, B = i B~ and the transform is -B~ + i A~;
+    // out_rot multiplies it by -i so that (A~, B~) is stored.
+    int out_rot;
 };
 
 template <typename T>
@@ -115,10 +119,12 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
         if (valid && pos < p.n_out) {
+            C o = cscale(v[q], p.scale);
+            if (p.out_rot) o = cmake<C>(o.y, -o.x);
             if (p.use_peers)
-                p.out_peer[pos / p.out_split][dst_off + (long long)(pos % p.out_split) * p.out_sline] = cscale(v[q], p.scale);
+                p.out_peer[pos / p.out_split][dst_off + (long long)(pos % p.out_split) * p.out_sline] = o;
             else
-                p.out[dst_off + line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = cscale(v[q], p.scale);
+                p.out[dst_off + line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = o;
         }
     }
 }
@@ -476,6 +482,9 @@ struct XParams {
     int PX;                 // pitch of the complex lines
     long long real_scomp, cplx_scomp;  // blockIdx.y selects the field component
     T scale;
+    // generator variant only: the generated lines are even (odd) about index 0, so their spectrum is purely real
+    // (imaginary); real_out = 1 (2) stores just that part as a REAL line of pitch PX (columns ninner..PX-1 zeroed)
+    int real_out;
 };
 
 template <typename T, int N, bool GEN>
@@ -533,6 +542,28 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
     C* oa = static_cast<C*>(p.out) + (long long)blockIdx.y * p.cplx_scomp + la * p.PX;
     C* ob = static_cast<C*>(p.out) + (long long)blockIdx.y * p.cplx_scomp + lb * p.PX;
     const T half = (T)0.5;
+    if constexpr (GEN) {
+        if (p.real_out) {
+            T* ra = static_cast<T*>(p.out) + la * p.PX;
+            T* rb = static_cast<T*>(p.out) + lb * p.PX;
+            const bool re = p.real_out == 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = j + q * TPL;
+                const C zk = v[q];
+                const C zm = lay.ld((N - k) & (N - 1));
+                if (va) ra[k] = re ? (zk.x + zm.x) * half : (zk.y - zm.y) * half;
+                if (vb) rb[k] = re ? (zk.y + zm.y) * half : (zm.x - zk.x) * half;
+            }
+            // Nyquist bin (real for a real line; zero for an odd one), then zeros up to the pitch
+            for (int k = N / 2 + j; k < p.PX; k += TPL) {
+                const bool nyq = (k == N / 2) && re;   // thread 0 holds bin N/2 in v[4]
+                if (va) ra[k] = nyq ? v[4].x : (T)0;
+                if (vb) rb[k] = nyq ? v[4].y : (T)0;
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int k = j + q * TPL;

@@ -107,6 +107,12 @@ __global__ void k_green_compress_free(T* __restrict__ S, const double2* __restri
     S[idx] = kx < ninner ? (T)(take_real ? spec[idx].x : spec[idx].y) : (T)0;
 }
 
+// real-symmetric build, Float32 meshes: the passes run in double, the cached spectrum is Float32
+__global__ void k_green_real_to_f32(float* __restrict__ S, const double* __restrict__ spec, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) S[idx] = (float)spec[idx];
+}
+
 template <typename T>
 __global__ void k_green_convert_full(cx_t<T>* __restrict__ G, const double2* __restrict__ spec, int ninner, int PX, long long total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,6 +141,11 @@ cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P
 cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cudaStream_t s) {
     const long long nd = (long long)(g.cnt[0] - 1) * (g.cnt[1] - 1) * (g.cnt[2] - 1);
     k_green_diff<<<blocks_for(nd, 256), 256, 0, s>>>(D, P, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_real_to_f32(void* S, const double* spec, long long total, cudaStream_t s) {
+    k_green_real_to_f32<<<blocks_for(total, 256), 256, 0, s>>>((float*)S, spec, total);
     return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ def test_header_declares_the_reference_surface():
     names = declared_symbols()
     # one entry point per reference function on the hot path
     for required in ("scb_clear", "scb_deposit", "scb_solve", "scb_solve_freespace", "scb_interpolate", "scb_green",
-                     "scb_bounds", "scb_create", "scb_destroy", "scb_last_error", "scb_step", "scb_step_host"):
+                     "scb_bounds", "scb_create", "scb_destroy", "scb_last_error", "scb_step", "scb_step_host", "scb_step_host_async", "scb_step_host_wait"):
         assert required in names
     assert len(names) >= 24
 

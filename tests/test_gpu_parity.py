@@ -248,6 +248,41 @@ def test_fused_and_host_steps_equal_the_separate_calls(scb):
     assert rel(mesh.efield.cpu().numpy(), e_want.cpu().numpy()) < 1e-12
 
 
+def test_pipelined_host_steps_equal_the_blocking_call(scb):
+    """scb_step_host_async / scb_step_host_wait: four bunches queued back to back (two staging slots, the
+    upload of one overlapping the download of the previous one) give the results of four blocking calls."""
+    import torch
+    grid = (20, 24, 28)
+    bunches = [gaussian(9000000 if k == 1 else 200000 + 1000 * k, 10 + k) for k in range(4)]   # one multi-chunk bunch
+    x0, y0, z0, _ = bunches[1]
+    mesh = scb.Mesh3D(grid, tuple(1.001 * a.min() for a in (x0, y0, z0)), tuple(1.001 * a.max() for a in (x0, y0, z0)))
+    inside = []
+    for (x, y, z, q) in bunches:   # keep every bunch inside the fixed mesh
+        m = np.ones(len(x), bool)
+        for a, lo, hi in zip((x, y, z), mesh.min_bounds, mesh.max_bounds):
+            m &= (a > lo) & (a < hi)
+        inside.append(tuple(np.ascontiguousarray(a[m]) for a in (x, y, z, q)))
+    want = []
+    for b in inside:
+        outs = [np.empty_like(b[0]) for _ in range(3)]
+        scb.step_host_(mesh, *b, *outs)
+        want.append(outs)
+    e_last = mesh.efield.clone()
+    got = [[np.full_like(b[0], np.nan) for _ in range(3)] for b in inside]
+    for rep in range(2):   # second round reuses both slots
+        for b, outs in zip(inside, got):
+            scb.step_host_async_(mesh, *b, *outs)
+        scb.step_host_wait_(mesh)
+        # the deposit accumulates with atomics, so two runs agree to rounding, not bit for bit
+        for outs, ref in zip(got, want):
+            for a, r in zip(outs, ref):
+                assert rel(a, r) < 1e-12
+        assert rel(mesh.efield.cpu().numpy(), e_last.cpu().numpy()) < 1e-12
+        for outs in got:
+            for a in outs:
+                a.fill(np.nan)
+
+
 def test_analytic_isotropic_gaussian(scb, record):
     """test/analytical_test.jl:20-50: max|Ez - Ez_analytic| / max|Ez_analytic| < 0.10 at 32^3."""
     from scipy.special import erf
