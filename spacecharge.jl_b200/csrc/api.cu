@@ -47,6 +47,10 @@ struct GreenEntry {
     long long scomp = 0;
     int ncomp = 3;        // 3: Ex,Ey,Ez; 4: + potential (icomp 0) as component 3
     unsigned long long stamp = 0;
+    // free space, Lz = 512: second copy of S with kz' fastest, St[((c*ninner + kx)*(Ly/2+1) + ky')*PZ + kz'], read by
+    // the even/odd-bin z pass (one contiguous row per line); t_off = byte offset inside data, 0 = absent
+    size_t t_off = 0;
+    int PZ = 0;
 };
 
 }  // namespace
@@ -315,6 +319,8 @@ Plan make_plan(const int64_t n[3]) {
 }
 
 // ---- Green spectrum: build (cold) and cache ------------------------------------------------
+// the even/odd-bin z pass (k_z_eo) exists for a padded z length of 512 (129..256 grid points along z)
+bool z_eo_eligible(const Plan& pl) { return pl.L[2] == 512; }
 // SCB_GREEN_REAL=0 selects the complex passes + compress kernel for the free-space build (A/B timing, debugging)
 bool real_sym_disabled() {
     static const bool off = [] { const char* e = getenv("SCB_GREEN_REAL"); return e && e[0] == '0'; }();
@@ -369,6 +375,13 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     ent.bytes = (size_t)ncomp * per_comp * elem;
     ent.scomp = (long long)per_comp;
     ent.ncomp = ncomp;
+    ent.t_off = 0;
+    ent.PZ = 0;
+    if (key.kind == 0 && z_eo_eligible(pl)) {
+        ent.PZ = (Lzh1 + 7) / 8 * 8;
+        ent.t_off = al(ent.bytes);
+        ent.bytes = ent.t_off + (size_t)ncomp * pl.ninner * Lyh1 * ent.PZ * elem;
+    }
     // reuse a retired buffer when one is large enough: cudaFree/cudaMalloc of ~0.5 GB blocks costs
     // anything from 1 to 400 ms on the host and would dominate a re-mesh-every-step workload
     ent.data = nullptr;
@@ -512,6 +525,14 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
             SCB_CUDA(h, launch_green_convert_full(dst, f64, final_spec, pl.ninner, pl.PX, (long long)per_comp, h->stream));
         h->launches += 7;
     }
+    if (ent.t_off) {
+        for (int c = 0; c < ncomp; ++c) {
+            const char* src = static_cast<const char*>(ent.data) + (size_t)c * per_comp * elem;
+            char* dstT = static_cast<char*>(ent.data) + ent.t_off + (size_t)c * pl.ninner * Lyh1 * ent.PZ * elem;
+            SCB_CUDA(h, launch_green_transpose(dstT, src, f64, pl.ninner, pl.PX, Lyh1, Lzh1, ent.PZ, h->stream));
+        }
+        h->launches += ncomp;
+    }
     return SCB_OK;
 }
 
@@ -618,7 +639,7 @@ scb_encode_tiled_fn tensor_map_encoder() {
 
 // dims / box in elements (innermost first), strides in bytes for dims 1..rank-1
 bool make_tensor_map(CUtensorMap* m, bool f64, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-                     const cuuint32_t* box) {
+                     const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
     scb_encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
@@ -626,8 +647,13 @@ bool make_tensor_map(CUtensorMap* m, bool f64, int rank, const void* base, const
     const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                       : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     return enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
-               const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool z_eo_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SCB_Z_EO"); return !e || std::atoi(e) != 0; }();
+    return on;
 }
 
 bool z_tma_enabled() {
@@ -724,7 +750,27 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         }
         const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
         bool done = false;
-        if (mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
+        if (mode == 0 && z_eo_enabled() && z_eo_eligible(pl) && gfree->t_off && gfree->PZ == ZEoLayout<T>::PZ) {
+            // even/odd-bin variant: one warp per line, 256-point transforms with a single exchange (see k_z_eo)
+            const bool f64 = sizeof(T) == 8;
+            const cuuint64_t s = sizeof(T), PX = pl.PX, L1 = pl.L[1], nz = pl.n[2];
+            const cuuint32_t TX = ZEoLayout<T>::TX;
+            const int rowb = ZEoLayout<T>::ROWB;
+            const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+            CUtensorMap mB, mC;
+            const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
+            const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
+            const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)szB * 2 * s};
+            const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
+            if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB, swz) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC, swz)) {
+                p.St = reinterpret_cast<const T*>(static_cast<const char*>(gfree->data) + gfree->t_off);
+                p.PZ = gfree->PZ;
+                SCB_CUDA(h, launch_z_eo<T>(p, mB, mC, h->stream));
+                done = true;
+            }
+        }
+        if (!done && mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
             // all global traffic of the pass through the TMA unit (see k_z_tma)
             const bool f64 = sizeof(T) == 8;
             const cuuint64_t s = sizeof(T), PX = pl.PX, L1 = pl.L[1], nz = pl.n[2];

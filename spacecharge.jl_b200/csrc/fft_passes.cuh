@@ -154,6 +154,9 @@ struct ZParams {
     // GREEN_FULL: G_c, complex, unfolded [kx + PX*(ky + Ly*kz)]
     const cx_t<T>* H;
     long long H_scomp;
+    // k_z_eo: copy of S with kz' fastest, St[((c*ninner + kx)*(Ly/2+1) + ky')*PZ + kz']
+    const T* St;
+    int PZ;
 };
 
 // cp.async of one real (4 or 8 bytes) from global to shared memory: lets the Green-spectrum
@@ -437,6 +440,262 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
 }
 
 // ------------------------------------------------------------------------------------------
+// fused z pass, even/odd-bin variant (free space, single GPU, padded length 512)
+//
+// ncu on k_z_tma (config 5, Float64): the LSU data pipe (67 %) and the FP64 pipe (50 %) share the kernel, and ~90 % of
+// the LSU wavefronts are the two shared-memory exchanges of each of the four 512-point transforms, separated by
+// block-wide barriers.  Here the 512-point transform of the zero-padded line is never formed:
+//     X[2k]   = FFT256(x)[k],   X[2k+1] = FFT256(x * w512^n)[k]                     (no arithmetic on the padding)
+//     y[n<256] = IFFT256(W_even)[n] + w512^-n * IFFT256(W_odd)[n]                   (no arithmetic on discarded outputs)
+// and each 256-point transform runs on 16 threads x 16 values as radix-16 x radix-16 with ONE exchange.  A line is
+// owned by one warp: lanes 0-15 carry the even bins, lanes 16-31 the odd ones, so every exchange is warp-local
+// (__syncwarp, no block barrier), the per-thread factor w512^(+-t) of the odd half folds into the inter-stage twiddle,
+// and the two halves meet in one shuffle step.  Shared-memory traffic per line drops from 16 to 8 exchange halves.
+// The Green spectrum is read from its kz'-fastest copy (one contiguous row per line and component, 1-D bulk copy);
+// input and output tiles travel as bulk tensor copies with a hardware swizzle so that a warp reads / writes its column
+// of the [z][kx] tile without bank conflicts.  tools/z_evenodd_model.py is the NumPy model of this schedule.
+template <int DIR, typename C> __device__ __forceinline__ C cmul_c(C v, typename real_of<C>::type cr, typename real_of<C>::type ci_fwd) {
+    using R = typename real_of<C>::type;
+    const R ci = DIR < 0 ? ci_fwd : -ci_fwd;
+    return cmake<C>(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
+}
+
+// 16-point DFT, natural order in and out: 4 x 4 with the twiddles w16^(q0*k0) as literals
+template <int DIR, typename C> __device__ __forceinline__ void dft16(C (&v)[16]) {
+    using R = typename real_of<C>::type;
+    const R c1 = (R)0.92387953251128675613, s1 = (R)0.38268343236508977173, hh = (R)0.70710678118654752440;
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0) dft4<DIR>(v[q0], v[q0 + 4], v[q0 + 8], v[q0 + 12]);
+    v[5] = cmul_c<DIR>(v[5], c1, -s1);     // w16^1
+    v[9] = cmul_c<DIR>(v[9], hh, -hh);     // w16^2
+    v[13] = cmul_c<DIR>(v[13], s1, -c1);   // w16^3
+    v[6] = cmul_c<DIR>(v[6], hh, -hh);     // w16^2
+    v[10] = cmul_qturn<DIR>(v[10]);        // w16^4
+    v[14] = cmul_c<DIR>(v[14], -hh, -hh);  // w16^6
+    v[7] = cmul_c<DIR>(v[7], s1, -c1);     // w16^3
+    v[11] = cmul_c<DIR>(v[11], -hh, -hh);  // w16^6
+    v[15] = cmul_c<DIR>(v[15], -c1, s1);   // w16^9
+#pragma unroll
+    for (int k0 = 0; k0 < 4; ++k0) dft4<DIR>(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);
+    // X[k0 + 4*k1] sits in v[4*k0 + k1]: transpose the 4 x 4 index
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            const C tmp = v[4 * a + b];
+            v[4 * a + b] = v[4 * b + a];
+            v[4 * b + a] = tmp;
+        }
+}
+
+// v[k] *= p0 * b^k, k = 0..15, the powers formed in two interleaved chains (even / odd k)
+template <typename C> __device__ __forceinline__ void apply_powers16(C (&v)[16], C p0, C b) {
+    const C b2 = cmul(b, b);
+    C pe = p0, po = cmul(p0, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[2 * k] = cmul(v[2 * k], pe);
+        v[2 * k + 1] = cmul(v[2 * k + 1], po);
+        if (k < 7) {
+            pe = cmul(pe, b2);
+            po = cmul(po, b2);
+        }
+    }
+}
+
+// 16 x 16 transpose among the 16 threads of a half-warp through its private buffer (pitch 17: conflict-free both ways)
+template <typename C> __device__ __forceinline__ void exchange16(C (&v)[16], C* ex, int t) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ex[k * 17 + t] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = ex[t * 17 + k];
+}
+
+// v[q] *= w32^(DIR * -q)... forward (DIR = -1): exp(-2 pi i q / 32); inverse: the conjugate
+template <int DIR, typename C> __device__ __forceinline__ void mul_w32_powers(C (&v)[16]) {
+    using R = typename real_of<C>::type;
+    // cos / sin of q*pi/16, q = 1..7
+    const R c[8] = {(R)1.0, (R)0.98078528040323044913, (R)0.92387953251128675613, (R)0.83146961230254523708,
+                    (R)0.70710678118654752440, (R)0.55557023301960222474, (R)0.38268343236508977173, (R)0.19509032201612826785};
+    const R s[8] = {(R)0.0, (R)0.19509032201612826785, (R)0.38268343236508977173, (R)0.55557023301960222474,
+                    (R)0.70710678118654752440, (R)0.83146961230254523708, (R)0.92387953251128675613, (R)0.98078528040323044913};
+#pragma unroll
+    for (int q = 1; q < 8; ++q) v[q] = cmul_c<DIR>(v[q], c[q], -s[q]);
+    v[8] = cmul_qturn<DIR>(v[8]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) v[q] = cmul_c<DIR>(v[q], -s[q - 8], -c[q - 8]);   // w32^(8+r) = -i * w32^r
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#ifndef SCB_ZEO_TX
+#define SCB_ZEO_TX 4
+#endif
+#ifndef SCB_ZEO_MINBLOCKS
+#define SCB_ZEO_MINBLOCKS 2
+#endif
+#ifndef SCB_ZEO_MINBLOCKS_F32
+#define SCB_ZEO_MINBLOCKS_F32 4
+#endif
+template <typename T> __host__ __device__ constexpr int zeo_minblocks() { return sizeof(T) == 4 ? SCB_ZEO_MINBLOCKS_F32 : SCB_ZEO_MINBLOCKS; }
+
+template <typename T>
+struct ZEoLayout {
+    using C = cx_t<T>;
+    static constexpr int N = 512, M = 256, TX = SCB_ZEO_TX, PZ = 264;     // TX lines (= warps) per CTA
+    static constexpr int ROWB = TX * (int)sizeof(C);                      // bytes per z row of the tile: 32 / 64 / 128
+    static constexpr unsigned SWZ_MASK = ROWB / 16 - 1;                   // SWIZZLE_32B / _64B / _128B
+    static constexpr size_t TILE = (size_t)M * ROWB;                      // one [z][kx] tile
+    static constexpr size_t EX = (size_t)TX * 2 * 16 * 17 * sizeof(C);    // one exchange buffer per half-warp
+    static constexpr size_t SB = (size_t)TX * 2 * PZ * sizeof(T);         // two spectrum rows per warp
+    static constexpr size_t BARS = 3 * TILE + EX + SB;                    // two input tiles + output staging first
+    static constexpr size_t BYTES = BARS + 128 + 1024;                    // barriers + slack for the 1 KB alignment
+    // byte offset of element (z row n, column w) inside a swizzled tile (tile base 1 KB aligned)
+    __device__ static __forceinline__ unsigned off(int n, int w) {
+        const unsigned o = (unsigned)n * ROWB + (unsigned)w * (unsigned)sizeof(C);
+        return o ^ (((o >> 7) & SWZ_MASK) << 4);
+    }
+};
+
+// One [z][kx] tile per CTA (a persistent variant that prefetched the next input tiles measured slower: 1.22 vs 0.94 ms;
+// the hardware's in-order CTA dispatch keeps neighbouring kx tiles, which share 128-byte lines, in flight together).
+// Three tile buffers: [0] receives the input and, once every warp has taken its line out of it, serves as output
+// staging for component 2; components 0 and 1 are staged in [1] and [2] -- so no component waits for the bulk store of
+// the previous one to drain its buffer (a potential as fourth component reuses [1] after the first store has read it).
+template <typename T>
+__global__ void __launch_bounds__(32 * SCB_ZEO_TX, zeo_minblocks<T>())
+k_z_eo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC, const ZParams<T> p) {
+    using C = cx_t<T>;
+    using LY = ZEoLayout<T>;
+    constexpr int N = LY::N, TX = LY::TX, PZ = LY::PZ;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int h = lane >> 4, t = lane & 15;
+    const bool leader = threadIdx.x == 0;
+    const int kx0 = blockIdx.x * TX, kx = kx0 + w;
+    int kyl;   // ky / Ly-ky back to back: they read the same folded spectrum rows (L2 reuse)
+    {
+        const int b = blockIdx.y, m = b >> 1;
+        kyl = b == 0 ? 0 : b == 1 ? p.Ly / 2 : (b & 1) ? p.Ly - m : m;
+    }
+    const int ky = kyl, Lyh = p.Ly / 2;
+    const int kyf = ky <= Lyh ? ky : p.Ly - ky;
+    const bool valid = kx < p.ninner;   // warp-uniform
+    C* ex = reinterpret_cast<C*>(smem_raw + 3 * LY::TILE) + (w * 2 + h) * (16 * 17);
+    T* sbuf = reinterpret_cast<T*>(smem_raw + 3 * LY::TILE + LY::EX) + (size_t)w * 2 * PZ;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + LY::BARS);   // [0] input, [1 + 2w + b] spectrum
+    unsigned long long* sbar = bars + 1 + 2 * w;
+    const unsigned tile_bytes = (unsigned)p.nz * LY::ROWB;
+    const unsigned s_bytes = (unsigned)PZ * sizeof(T);
+
+    auto load_S = [&](int c) {   // lane 0 of a valid warp
+        const T* src = p.St + (((long long)c * p.ninner + kx) * (Lyh + 1) + kyf) * PZ;
+        mbar_expect_tx(sbar + (c & 1), s_bytes);
+        bulk_load_1d(sbuf + (c & 1) * PZ, src, s_bytes, sbar + (c & 1));
+    };
+
+    if (leader) {
+#pragma unroll
+        for (int i = 0; i < 1 + 2 * TX; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (leader) {
+        mbar_expect_tx(bars + 0, tile_bytes);
+        tma_load_3d(smem_raw, &mapB, 2 * kx0, kyl, 0, bars + 0);
+    }
+    if (valid && lane == 0) {
+        load_S(0);
+        if (p.ncomp > 1) load_S(1);
+    }
+    // per-thread roots (table: exp(-2 pi i k / 512)): w256^t, w512^t (odd half), w512^(2t+h)
+    const C bf = __ldg(p.tw + 2 * t);
+    const C cf = h ? __ldg(p.tw + t) : cmake<C>(1, 0);
+    const C bi = cconj(__ldg(p.tw + 2 * t + h));
+
+    C spec[16];
+    mbar_wait(bars + 0, 0);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = t + 16 * q;
+        spec[q] = (valid && n < p.nz) ? *reinterpret_cast<const C*>(smem_raw + LY::off(n, w)) : cmake<C>(0, 0);
+    }
+    __syncthreads();   // every warp holds its line: buffer 0 may be overwritten by output staging from here on
+#ifndef SCB_ZEO_NOCOMPUTE
+    if (valid) {
+        if (h) mul_w32_powers<-1>(spec);
+        dft16<-1>(spec);
+        apply_powers16(spec, cf, bf);
+        exchange16(spec, ex, t);
+        dft16<-1>(spec);   // spec[k2] = bin 2*(t + 16*k2) + h
+    }
+#endif
+
+#pragma unroll 1
+    for (int c = 0; c < p.ncomp; ++c) {
+        C y[8];
+        if (valid) {
+            C wv[16];
+            mbar_wait(sbar + (c & 1), (c >> 1) & 1);
+            const T* sb = sbuf + (c & 1) * PZ;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                const int b = 2 * (t + 16 * k2) + h;
+                const int kzf = b <= N / 2 ? b : N - b;
+                T s = sb[kzf];
+                if ((c == 1 && ky > Lyh) || (c == 2 && b > N / 2)) s = -s;
+                // field: (a + ib) * (i s) = s * (-b + i a);  potential: (a + ib) * s
+                wv[k2] = c == 3 ? cmake<C>(spec[k2].x * s, spec[k2].y * s) : cmake<C>(-spec[k2].y * s, spec[k2].x * s);
+            }
+            __syncwarp();
+            if (lane == 0 && c + 2 < p.ncomp) load_S(c + 2);   // the whole warp is past its reads of this row
+#ifndef SCB_ZEO_NOCOMPUTE   // (timing experiment: memory traffic of the pass without its arithmetic)
+            dft16<+1>(wv);
+            apply_powers16(wv, cmake<C>(1, 0), bi);
+            exchange16(wv, ex, t);
+            dft16<+1>(wv);   // wv[n2] = half h of y[t + 16*n2]
+            if (h) mul_w32_powers<+1>(wv);
+#endif
+            // even half + odd half: lanes 0-15 keep n2 = 0..7, lanes 16-31 keep n2 = 8..15
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const C snd = h ? wv[i] : wv[8 + i];
+                const C keep = h ? wv[8 + i] : wv[i];
+                C got;
+                got.x = __shfl_xor_sync(0xffffffffu, snd.x, 16);
+                got.y = __shfl_xor_sync(0xffffffffu, snd.y, 16);
+                y[i] = h ? cadd(got, keep) : cadd(keep, got);   // even part + odd part on both halves
+            }
+        }
+        unsigned char* stage = smem_raw + (size_t)((c + 1) % 3) * LY::TILE;
+        if (c >= 3) {   // fourth component: its buffer was handed to the store of component c-3
+            if (leader) bulk_wait_read<2>();
+            __syncthreads();
+        }
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = t + 16 * (8 * h + i);
+                if (n < p.nz) *reinterpret_cast<C*>(stage + LY::off(n, w)) = y[i];
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (leader) {
+            tma_store_4d(&mapC, 2 * kx0, kyl, 0, c, stage);
+            bulk_commit();
+        }
+    }
+    if (leader) bulk_wait_read<0>();   // shared memory must outlive the stores that read it
+}
+
+// ------------------------------------------------------------------------------------------
 // x passes: real <-> half-complex along the contiguous axis, two real lines per transform
 // Generator for the x pass of the Green-spectrum build: the padded, wrap-around-placed IGF array is
 // never materialised; element (X, Y, Z) is produced on the fly from the table D of differenced values
@@ -638,6 +897,7 @@ template <typename T> cudaError_t launch_z_fused(int N, int kind, const ZParams<
 template <typename T> cudaError_t launch_z_tma(int N, const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC,
                                                 const CUtensorMap& mapS, cudaStream_t s);
 
+template <typename T> cudaError_t launch_z_eo(const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s);
 template <typename T> cudaError_t launch_x_r2c(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 template <typename T> cudaError_t launch_x_c2r(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 bool fft_len_supported(int N);

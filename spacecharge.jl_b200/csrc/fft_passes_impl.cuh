@@ -72,6 +72,14 @@ template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p, cons
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+template <> cudaError_t launch_z_eo<SCB_T>(const ZParams<SCB_T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s) {
+    using LY = ZEoLayout<SCB_T>;
+    dim3 grid((p.ninner + LY::TX - 1) / LY::TX, p.Ly), block(32 * LY::TX);
+    cudaError_t e = set_smem(k_z_eo<SCB_T>, LY::BYTES);
+    if (e == cudaSuccess) k_z_eo<SCB_T><<<grid, block, LY::BYTES, s>>>(mapB, mapC, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 template <> cudaError_t launch_x_r2c<SCB_T>(int N, const XParams<SCB_T>& p, int ncomp, cudaStream_t s) {
     using C = cx_t<SCB_T>;
     cudaError_t e = cudaErrorInvalidValue;

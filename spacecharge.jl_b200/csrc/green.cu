@@ -107,6 +107,27 @@ __global__ void k_green_compress_free(T* __restrict__ S, const double2* __restri
     S[idx] = kx < ninner ? (T)(take_real ? spec[idx].x : spec[idx].y) : (T)0;
 }
 
+// S[kx + PX*(ky + Lyh1*kz)] -> St[(kx*Lyh1 + ky)*PZ + kz] (kz fastest): 32 x 32 tiles over (kx, kz) for each ky
+template <typename T>
+__global__ void __launch_bounds__(256) k_green_transpose(T* __restrict__ St, const T* __restrict__ S, int ninner, int PX, int Lyh1,
+                                                          int Lzh1, int PZ) {
+    __shared__ T tile[32][33];
+    const int ky = blockIdx.z;
+    const int kx0 = blockIdx.x * 32, kz0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int kz = kz0 + ty + 8 * r, kx = kx0 + tx;
+        tile[ty + 8 * r][tx] = (kz < Lzh1 && kx < ninner) ? S[kx + (long long)PX * (ky + (long long)Lyh1 * kz)] : (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int kx = kx0 + ty + 8 * r, kz = kz0 + tx;
+        if (kx < ninner && kz < PZ) St[((long long)kx * Lyh1 + ky) * PZ + kz] = tile[tx][ty + 8 * r];
+    }
+}
+
 // real-symmetric build, Float32 meshes: the passes run in double, the cached spectrum is Float32
 __global__ void k_green_real_to_f32(float* __restrict__ S, const double* __restrict__ spec, long long total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,6 +162,13 @@ cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P
 cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cudaStream_t s) {
     const long long nd = (long long)(g.cnt[0] - 1) * (g.cnt[1] - 1) * (g.cnt[2] - 1);
     k_green_diff<<<blocks_for(nd, 256), 256, 0, s>>>(D, P, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_green_transpose(void* St, const void* S, int dt_f64, int ninner, int PX, int Lyh1, int Lzh1, int PZ, cudaStream_t s) {
+    dim3 grid((ninner + 31) / 32, (PZ + 31) / 32, Lyh1);
+    if (dt_f64) k_green_transpose<double><<<grid, 256, 0, s>>>((double*)St, (const double*)S, ninner, PX, Lyh1, Lzh1, PZ);
+    else k_green_transpose<float><<<grid, 256, 0, s>>>((float*)St, (const float*)S, ninner, PX, Lyh1, Lzh1, PZ);
     return cudaGetLastError();
 }
 

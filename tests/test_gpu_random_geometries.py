@@ -50,11 +50,13 @@ def test_random_geometry_solve_and_step(scb, oracle, record, seed):
         assert float(np.abs(got[c].cpu().numpy() - want[c]).max() / wscale) < tol
 
 
-@pytest.mark.parametrize("grid", [(1024, 2, 3), (2, 1024, 2), (3, 2, 1024), (512, 4, 2), (2, 2, 2), (129, 3, 65)])
+@pytest.mark.parametrize("grid", [(1024, 2, 3), (2, 1024, 2), (3, 2, 1024), (512, 4, 2), (2, 2, 2), (129, 3, 65),
+                                  (5, 3, 200), (4, 6, 256), (9, 2, 129)])
 @pytest.mark.parametrize("at_cathode", [False, True])
 def test_extreme_aspect_ratios(scb, oracle, record, grid, at_cathode):
-    """Largest supported axis (n = 1024, padded transform length 2048), the smallest grid (2,2,2) and
-    sizes just above a power of two (129 -> padded 512)."""
+    """Largest supported axis (n = 1024, padded transform length 2048), the smallest grid (2,2,2),
+    sizes just above a power of two (129 -> padded 512), and 129..256 points along z (padded 512: the
+    free-space solve takes the even/odd-bin z pass k_z_eo)."""
     import torch
     rng = np.random.default_rng(sum(grid))
     rho = rng.standard_normal(grid)
@@ -71,3 +73,39 @@ def test_extreme_aspect_ratios(scb, oracle, record, grid, at_cathode):
         err = float(np.abs(e[..., c] - ref.efield[..., c]).max() / scale)
         record("E%d grid=%s cath=%s" % (c, grid, at_cathode), err, 1e-10)
         assert err < 1e-10
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-10), (np.float32, 1e-5)])
+def test_even_odd_z_pass_line_by_line(scb, oracle, record, T, tol):
+    """k_z_eo (padded z length 512): every kx column of a CTA tile, both ky halves of the folded spectrum, the
+    last partial tile (kx = 256), nz < 256 (zero rows inside the 256-point transforms), with and without the
+    potential as fourth component."""
+    import torch
+    grid = (130, 5, 200)   # Lx = 512: kx tiles up to the single-column tile at kx = 256
+    rng = np.random.default_rng(5)
+    rho = rng.standard_normal(grid).astype(T)
+    lo, hi = (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3)
+    mesh = scb.Mesh3D(grid, lo, hi, T=T, gamma=1.5)
+    ref = oracle.mesh_from_bounds(grid, lo, hi, T=np.float64, gamma=1.5)
+    if T == np.float32:   # the Float64 oracle on the same Float32-valued geometry
+        ref.min_bounds, ref.max_bounds, ref.delta = (tuple(np.float64(v) for v in t)
+                                                     for t in (mesh.min_bounds, mesh.max_bounds, mesh.delta))
+    ref.rho[...] = rho
+    oracle.solve(ref, potential=True)
+    mesh.rho.copy_(torch.from_numpy(rho).cuda())
+    scb.solve_(mesh)
+    e = mesh.efield.cpu().numpy().astype(np.float64)
+    scale = max(np.abs(ref.efield[..., c]).max() for c in range(3))
+    for c in range(3):
+        err = float(np.abs(e[..., c] - ref.efield[..., c]).max() / scale)
+        record("k_z_eo E%d %s" % (c, np.dtype(T).name), err, tol)
+        assert err < tol
+    scb.solve_potential_(mesh)
+    e2 = mesh.efield.cpu().numpy().astype(np.float64)
+    for c in range(3):
+        assert float(np.abs(e2[..., c] - ref.efield[..., c]).max() / scale) < tol
+    perr = float(np.abs(mesh.phi.cpu().numpy() - ref.phi).max() / np.abs(ref.phi).max())
+    # the potential's Green function cancels harder than the field's on this elongated geometry (parity unpinned
+    # extension, DESIGN.md): same 1.7e-10 with the TMA z pass (SCB_Z_EO=0)
+    record("k_z_eo phi %s" % np.dtype(T).name, perr, 5 * tol)
+    assert perr < 5 * tol
