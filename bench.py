@@ -324,7 +324,8 @@ def main():
                          "frac": round(gbs / peak, 4)}
     kernel_names = {"deposit": "k_deposit_tiles", "interpolate": "k_interpolate_pair2_f64" if s == 8 else "k_interpolate_packed_f32",
                     "F1": "k_x_r2c", "F2": "k_lines<-1>",
-                    "Z": "k_z_tma" if (world == 1 and not at_cathode and grid[2] <= 256) else "k_z_fused",
+                    "Z": ("k_z_eo" if (world == 1 and not at_cathode and 128 < grid[2] <= 256) else
+                          "k_z_tma" if (world == 1 and not at_cathode and grid[2] <= 256) else "k_z_fused"),
                     "B2": "k_lines<+1>", "B3": "k_x_c2r"}
     dom = max(stage_roof, key=lambda k: stage_roof[k]["ms"])
     roofline = {"kernel": kernel_names[dom], "stage": dom, "bound": "hbm", "achieved": stage_roof[dom]["GBps"],
