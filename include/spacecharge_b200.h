@@ -198,6 +198,16 @@ SCB_API int scb_solve_sharded(scb_handle* h, const void* rho_partial, void* efie
                               const double max_bounds[3], const double delta[3], double gamma,
                               int at_cathode);
 
+/* deposit + scb_solve_sharded + interpolation in one call.  rho_partial receives this rank's partial
+ * charge grid, efield the complete field, ex/ey/ez the field at this rank's particles.
+ * SCB_GATHER_OVERLAP=1 (experimental, slower as measured) overlaps the all-gather of the field with the
+ * interpolation: the z slabs are broadcast one by one from the middle of the grid outwards, repacked as
+ * they land, and the gather runs in passes over the cells whose planes have arrived. */
+SCB_API int scb_step_sharded(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                     const void* q, int pdt, void* rho_partial, void* efield, int mdt,
+                     const int64_t n[3], const double min_bounds[3], const double max_bounds[3],
+                     const double delta[3], double gamma, int at_cathode, void* ex, void* ey, void* ez);
+
 /* ---- cache control ------------------------------------------------------------------------ */
 SCB_API int scb_drop_green_cache(scb_handle* h);
 /* bytes of device workspace currently owned by the handle */

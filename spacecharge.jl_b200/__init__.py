@@ -509,6 +509,14 @@ def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> Non
                                  mesh._hi(), mesh._d(), float(mesh.gamma), 1 if at_cathode else 0,
                                  ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
         return
+    if mesh.sharded:
+        # slab-decomposed solve with the all-gather of the field overlapped with the interpolation
+        hd.init_comm(mesh.group)
+        hd.check(hd.lib.scb_step_sharded(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(),
+                                         _tag(x.dtype), mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(),
+                                         mesh._n(), mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma),
+                                         1 if at_cathode else 0, ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+        return
     deposit_(mesh, x, y, z, q)
     solve_(mesh, at_cathode=at_cathode)
     hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),

@@ -100,6 +100,9 @@ struct scb_handle {
     cudaEvent_t slot_out_free[2] = {nullptr, nullptr};   // d2h stream: last copy that reads the slot's ex,ey,ez
     bool slot_used[2] = {false, false};
     int host_steps_in_flight = 0;
+    // slab-decomposed step: field slabs broadcast on comm_stream, repacked on pack_stream, gathered on the main stream
+    cudaStream_t comm_stream = nullptr, pack_stream = nullptr;
+    cudaEvent_t ev_field = nullptr, ev_bcast[SCB_MAX_RANKS] = {}, ev_pack[SCB_MAX_RANKS] = {};
 };
 
 namespace {
@@ -139,6 +142,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -162,6 +166,7 @@ bool load_nccl() {
     SCB_SYM(Recv, "ncclRecv")
     SCB_SYM(GroupStart, "ncclGroupStart")
     SCB_SYM(GroupEnd, "ncclGroupEnd")
+    SCB_SYM(Broadcast, "ncclBroadcast")
     SCB_SYM(GetErrorString, "ncclGetErrorString")
 #undef SCB_SYM
     g_nccl.dl = dl;
@@ -925,7 +930,10 @@ int scb_destroy(scb_handle* h) {
     if (!h) return SCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream})
+    for (cudaEvent_t e : h->ev_bcast) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_pack) if (e) cudaEventDestroy(e);
+    if (h->ev_field) cudaEventDestroy(h->ev_field);
+    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream, h->comm_stream, h->pack_stream})
         if (cs) {
             cudaStreamSynchronize(cs);
             cudaStreamDestroy(cs);
@@ -1388,7 +1396,7 @@ int all_to_all(scb_handle* h, const char* send, char* recv, size_t block_bytes, 
 
 template <typename T>
 int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan& pl, const double delta[3], double gamma,
-                      int mode, const double offset[3]) {
+                      int mode, const double offset[3], bool defer_gather = false) {
     using C = cx_t<T>;
     const int G = h->nranks, me = h->rank;
     const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
@@ -1495,13 +1503,87 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
         p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
         SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
     }
-    SCB_NCCL(h, g_nccl.GroupStart());
-    for (int c = 0; c < 3; ++c)
-        SCB_NCCL(h, g_nccl.AllGather(efield + c * ng + (size_t)me * slab_elems, efield + c * ng, slab_elems, nt, h->comm, h->stream));
-    SCB_NCCL(h, g_nccl.GroupEnd());
+    if (!defer_gather) {   // scb_step_sharded gathers the slabs itself, overlapped with the interpolation
+        SCB_NCCL(h, g_nccl.GroupStart());
+        for (int c = 0; c < 3; ++c)
+            SCB_NCCL(h, g_nccl.AllGather(efield + c * ng + (size_t)me * slab_elems, efield + c * ng, slab_elems, nt, h->comm, h->stream));
+        SCB_NCCL(h, g_nccl.GroupEnd());
+    }
     tick(h, 13);
     h->t_pass = true;
     h->launches += 5 + 4;  // five pass kernels + four collectives
+    return SCB_OK;
+}
+
+// Field slabs -> every rank, overlapped with the gather.  The all-gather of E is receive-bound (every rank takes in
+// (G-1)/G of the 3*Ng field) and nothing is left to compute on the grid once the last pass has run, so the only work
+// that can hide it is the interpolation itself: the slabs are broadcast one by one from the middle of the grid
+// outwards (for a bunch the middle planes hold most particles), each is repacked node-major as it lands, and the
+// gather runs in passes over the cells whose two z planes have arrived -- after 2, 4, 8, ... slabs -- each pass
+// skipping the particles outside its z range (later passes read z alone and fetch x, y for the few they select).
+template <typename T>
+int gather_field_and_interpolate(scb_handle* h, T* efield, const Plan& pl, int64_t np, const void* x, const void* y, const void* z,
+                                 int pdt, const Geom3& g0, void* ex, void* ey, void* ez) {
+    const int G = h->nranks;
+    const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
+    const ncclDataType_t nt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+    const int nzl = pl.n[2] / G;
+    const long long ng = (long long)pl.n[0] * pl.n[1] * pl.n[2];
+    const size_t slab_elems = (size_t)pl.n[0] * pl.n[1] * nzl;
+    SCB_TRY(ensure_packed(h, (size_t)ng * packed_bytes_per_node(mdt)));
+    if (!h->comm_stream) {
+        // highest priority: the collectives' few CTAs must get onto the SMs as soon as gather CTAs of an earlier pass retire
+        int least = 0, greatest = 0;
+        SCB_CUDA(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SCB_CUDA(h, cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest));
+        SCB_CUDA(h, cudaStreamCreateWithPriority(&h->pack_stream, cudaStreamNonBlocking, greatest));
+    }
+    if (!h->ev_field) SCB_CUDA(h, cudaEventCreateWithFlags(&h->ev_field, cudaEventDisableTiming));
+    for (int i = 0; i < G; ++i) {
+        if (!h->ev_bcast[i]) SCB_CUDA(h, cudaEventCreateWithFlags(&h->ev_bcast[i], cudaEventDisableTiming));
+        if (!h->ev_pack[i]) SCB_CUDA(h, cudaEventCreateWithFlags(&h->ev_pack[i], cudaEventDisableTiming));
+    }
+    // middle-out slab order, identical on every rank: G/2-1, G/2, G/2-2, G/2+1, ...
+    int order[SCB_MAX_RANKS];
+    for (int i = 0, lo = G / 2 - 1, hi = G / 2; i < G;) {
+        if (lo >= 0) order[i++] = lo--;
+        if (hi < G && i < G) order[i++] = hi++;
+    }
+    SCB_CUDA(h, cudaEventRecord(h->ev_field, h->stream));          // this rank's slab is complete (B3)
+    SCB_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_field, 0));
+    for (int i = 0; i < G; ++i) {
+        const int sl = order[i];
+        SCB_NCCL(h, g_nccl.GroupStart());
+        for (int c = 0; c < 3; ++c) {
+            T* p = efield + c * ng + (size_t)sl * slab_elems;
+            SCB_NCCL(h, g_nccl.Broadcast(p, p, slab_elems, nt, sl, h->comm, h->comm_stream));
+        }
+        SCB_NCCL(h, g_nccl.GroupEnd());
+        SCB_CUDA(h, cudaEventRecord(h->ev_bcast[i], h->comm_stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->pack_stream, h->ev_bcast[i], 0));
+        SCB_CUDA(h, launch_pack_efield(mdt, efield, h->packed, g0, h->pack_stream, (long long)sl * slab_elems, (long long)slab_elems));
+        SCB_CUDA(h, cudaEventRecord(h->ev_pack[i], h->pack_stream));
+        h->launches += 2;
+    }
+    // gather passes: after `cnt` slabs the arrived planes form one block [a, b]; its cells are [a*nzl, (b+1)*nzl - 1)
+    int done = 0, prev_lo = 0, prev_hi = 0;
+    for (int cnt = (G == 2 ? 1 : 2); done < G; cnt = cnt * 2 > G ? G : cnt * 2) {
+        int a = G, b = -1;
+        for (int i = 0; i < cnt; ++i) { a = order[i] < a ? order[i] : a; b = order[i] > b ? order[i] : b; }
+        for (int i = done; i < cnt; ++i) SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_pack[i], 0));
+        Geom3 g = g0;
+        g.zlo = a * nzl;
+        g.zhi = (b + 1) * nzl - 1;
+        g.exlo = prev_lo;
+        g.exhi = prev_hi;
+        g.zfirst = done > 0 ? 1 : 0;
+        SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream));
+        h->launches += 1;
+        prev_lo = g.zlo;
+        prev_hi = g.zhi;
+        done = cnt;
+        if (cnt == G) break;
+    }
     return SCB_OK;
 }
 
@@ -1567,6 +1649,52 @@ int scb_solve_sharded(scb_handle* h, const void* rho_partial, void* efield, int 
         rc = run_solve_sharded<float>(h, (const float*)rho_partial, (float*)efield, pl, delta, gamma, at_cathode ? 1 : 0, offset);
     tick(h, 3);
     h->t_solve = rc == SCB_OK;
+    return rc;
+}
+
+int scb_step_sharded(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
+                     void* rho_partial, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                     const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* ex, void* ey,
+                     void* ez) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!h->comm) return fail(h, SCB_ERR_COMM, "scb_comm_init has not been called");
+    if (np < 0 || !rho_partial || !efield || !delta || !min_bounds || !max_bounds || !valid_dt(mdt) || !valid_dt(pdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_step_sharded");
+    if (np > 0 && (!x || !y || !z || !q || !ex || !ey || !ez)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    const Plan pl = make_plan(n);
+    if (pl.n[2] % h->nranks != 0 || pl.L[1] % h->nranks != 0)
+        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the padded y length must be multiples of the number of ranks");
+    // Opt-in (SCB_GATHER_OVERLAP=1, read on every call).  Measured on 2 GPUs at config 5: 6.38 ms per step against 5.11 ms
+    // for the plain sequence -- one-root broadcasts give up the all-links parallelism of the all-gather, and a filtered
+    // gather pass costs almost a full pass (every warp iteration still pays its latency) -- see DESIGN.md section 4.
+    const char* ov = std::getenv("SCB_GATHER_OVERLAP");
+    const bool overlap = ov && std::atoi(ov) != 0;
+    // the slab filter lives in the packed-field gather kernels (default interpolation mode)
+    const bool pipelined = overlap && h->nranks > 1 && interp_mode() == 0 && pl.n[2] / h->nranks >= 2;
+    SCB_TRY(scb_deposit(h, np, x, y, z, q, pdt, rho_partial, mdt, n, min_bounds, delta, 1));
+    if (!pipelined) {
+        SCB_TRY(scb_solve_sharded(h, rho_partial, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+        return scb_interpolate(h, np, x, y, z, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
+    }
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    double offset[3] = {0.0, 0.0, 0.0};
+    if (at_cathode) offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
+    tick(h, 2);
+    int rc;
+    if (mdt == SCB_F64)
+        rc = run_solve_sharded<double>(h, (const double*)rho_partial, (double*)efield, pl, delta, gamma, at_cathode ? 1 : 0, offset, true);
+    else
+        rc = run_solve_sharded<float>(h, (const float*)rho_partial, (float*)efield, pl, delta, gamma, at_cathode ? 1 : 0, offset, true);
+    tick(h, 3);
+    h->t_solve = true;
+    if (rc != SCB_OK) return rc;
+    tick(h, 4);
+    const Geom3 g = make_geom(n, min_bounds, delta);
+    if (mdt == SCB_F64) rc = gather_field_and_interpolate<double>(h, (double*)efield, pl, np, x, y, z, pdt, g, ex, ey, ez);
+    else rc = gather_field_and_interpolate<float>(h, (float*)efield, pl, np, x, y, z, pdt, g, ex, ey, ez);
+    tick(h, 5);
+    h->t_interp = true;
     return rc;
 }
 

@@ -22,6 +22,10 @@ struct Geom3 {
     double delta[3];
     int n[3];
     int l2_keep = 1;   // 1: grid-side accesses of the particle passes carry an L2 evict_last policy (SCB_L2_HINT=0 disables)
+    // gather kernels only: handle the particles whose z cell lies in [zlo, zhi) but not in [exlo, exhi) -- the
+    // slab-decomposed step interpolates while the field slabs are still arriving.  zfirst: read z alone, fetch x and y
+    // only for the selected particles (passes that select few of them).
+    int zlo = 0, zhi = 0x7fffffff, exlo = 0, exhi = 0, zfirst = 0;
 };
 
 // fused momentum kick of the gather kernels: off = plain interpolate_field (outputs overwritten)
@@ -54,7 +58,9 @@ cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, co
                                const Kick& kick = Kick());
 // node-major repack of efield (32 bytes per node) and the gather that reads it
 size_t packed_bytes_per_node(int mdt);   // node-major record size
-cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s);
+int interp_mode();   // SCB_INTERP_MODE: 0 = default gather kernels
+cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s,
+                               long long first_node = 0, long long count = -1);
 cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                       const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
                                       const Kick& kick = Kick());

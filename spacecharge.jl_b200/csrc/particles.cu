@@ -53,6 +53,13 @@ __device__ __forceinline__ void locate(W px, W py, W pz, const Geom3& g, CellW<W
     }
 }
 
+// z cell of a particle (same arithmetic as locate) and the slab filter of the gather kernels
+template <typename W> __device__ __forceinline__ bool z_selected(W pz, const Geom3& g) {
+    const W t = (pz - (W)g.lo[2]) / (W)g.delta[2];
+    const int iz = (int)fmin(fmax(floor(t), (W)0), (W)(g.n[2] - 2));
+    return iz >= g.zlo && iz < g.zhi && !(iz >= g.exlo && iz < g.exhi);
+}
+
 // ---- deposit: one thread per particle, eight reductions into rho --------------------------
 template <typename P, typename T>
 __global__ void __launch_bounds__(256) k_deposit(long long np, const P* __restrict__ x, const P* __restrict__ y,
@@ -267,16 +274,16 @@ __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __re
 // The arithmetic (weights, order of the eight products, left-to-right sum) is unchanged, so the
 // results are bit-identical to k_interpolate.
 __global__ void __launch_bounds__(256) k_pack_efield_f64(const double* __restrict__ e, double4* __restrict__ out,
-                                                          long long ng) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ng) return;
+                                                          long long ng, long long first, long long count) {
+    const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= first + count) return;
     out[i] = make_double4(__ldg(e + i), __ldg(e + ng + i), __ldg(e + 2 * ng + i), 0.0);
 }
 
 __global__ void __launch_bounds__(256) k_pack_efield_f32(const float* __restrict__ e, float4* __restrict__ out,
-                                                          long long ng, int nx) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ng) return;
+                                                          long long ng, int nx, long long first, long long count) {
+    const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= first + count) return;
     const bool last = (int)(i % nx) == nx - 1;
     const float4 a = make_float4(__ldg(e + i), __ldg(e + ng + i), __ldg(e + 2 * ng + i), 0.f);
     const float4 b = last ? make_float4(0.f, 0.f, 0.f, 0.f)
@@ -432,15 +439,24 @@ __global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, con
     // latency-bound (ncu: long-scoreboard stalls 12 per issued instruction), and this takes the DRAM round trip of the
     // particle stream off the critical path of every iteration
     long long i = warp * 16 + (lane >> 1);
+    const bool filt = g.zlo > 0 || g.zhi < g.n[2];   // slab filter active (uniform)
+    const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
-    if (i < np) { cx = ld_stream(x + i); cy = ld_stream(y + i); cz = ld_stream(z + i); }
+    if (i < np) {
+        cz = ld_stream(z + i);
+        if (!zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+    }
     for (; __any_sync(FULL, i < np); i += nwarps * 16) {
-        const bool live = i < np;
         const long long inext = i + nwarps * 16;
         P nx_ = 0, ny_ = 0, nz_ = 0;
-        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); }
+        if (inext < np) {
+            nz_ = ld_stream(z + inext);
+            if (!zfirst) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); }
+        }
+        const bool live = i < np && (!filt || z_selected<W>((W)cz, g));
         W acc[3] = {0, 0, 0};
         if (live) {
+            if (zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
             CellW<W> c;
             locate<W>((W)cx, (W)cy, (W)cz, g, c);
             const double4* b = e + (c.i[0] + sy * c.i[1] + sz * c.i[2]) + kx;
@@ -484,12 +500,25 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
     const unsigned long long pol = l2_policy(g.l2_keep);
     // coordinates requested one iteration ahead (latency-bound gather, see k_interpolate_pair2_f64)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool filt = g.zlo > 0 || g.zhi < g.n[2];   // slab filter active (uniform)
+    const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
-    if (i < np) { cx = ld_stream(x + i); cy = ld_stream(y + i); cz = ld_stream(z + i); }
+    if (i < np) {
+        cz = ld_stream(z + i);
+        if (!zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+    }
     for (; i < np; i += stride) {
         const long long inext = i + stride;
         P nx_ = 0, ny_ = 0, nz_ = 0;
-        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); }
+        if (inext < np) {
+            nz_ = ld_stream(z + inext);
+            if (!zfirst) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); }
+        }
+        if (filt && !z_selected<W>((W)cz, g)) {
+            cx = nx_; cy = ny_; cz = nz_;
+            continue;
+        }
+        if (zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
         CellW<W> c;
         locate<W>((W)cx, (W)cy, (W)cz, g, c);
         const float4* b = e + 2 * (c.i[0] + sy * c.i[1] + sz * c.i[2]);
@@ -664,11 +693,14 @@ int interp_mode() {
 
 size_t packed_bytes_per_node(int) { return 32; }
 
-cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s) {
+cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const Geom3& g, cudaStream_t s, long long first,
+                               long long count) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
-    const unsigned grid = (unsigned)((ng + 255) / 256);
-    if (mdt == 1) k_pack_efield_f64<<<grid, 256, 0, s>>>((const double*)efield, (double4*)packed, ng);
-    else k_pack_efield_f32<<<grid, 256, 0, s>>>((const float*)efield, (float4*)packed, ng, g.n[0]);
+    if (count < 0) count = ng - first;
+    if (count <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (mdt == 1) k_pack_efield_f64<<<grid, 256, 0, s>>>((const double*)efield, (double4*)packed, ng, first, count);
+    else k_pack_efield_f32<<<grid, 256, 0, s>>>((const float*)efield, (float4*)packed, ng, g.n[0], first, count);
     return cudaGetLastError();
 }
 

@@ -55,6 +55,19 @@ def _worker(rank, world, port, out_dir):
                 assert err < tol, (grid, cath, sharded, c, err)
                 err = float((out[c] - rex[c]).abs().max() / rex[c].abs().max())
                 assert err < tol, (grid, cath, sharded, "interp", c, err)
+            # fused step; in the sharded mode also with the field slabs broadcast and gathered in overlapping passes
+            for overlap in ("0", "1"):
+                os.environ["SCB_GATHER_OVERLAP"] = overlap
+                outs = [torch.full_like(mine[0], float("nan")) for _ in range(3)]
+                mesh.efield.zero_()
+                scb.step_(mesh, *mine, *outs, at_cathode=cath)
+                torch.cuda.synchronize()
+                for c in range(3):
+                    err = float((outs[c] - rex[c]).abs().max() / rex[c].abs().max())
+                    assert err < tol, (grid, cath, sharded, overlap, "step interp", c, err)
+                    err = float((mesh.efield[..., c] - ref.efield[..., c]).abs().max() / ref.efield[..., c].abs().max())
+                    assert err < tol, (grid, cath, sharded, overlap, "step field", c, err)
+            os.environ.pop("SCB_GATHER_OVERLAP", None)
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("%g" % worst)
     dist.destroy_process_group()
 
