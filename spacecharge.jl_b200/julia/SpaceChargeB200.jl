@@ -272,4 +272,32 @@ function step!(mesh::Mesh3D{T}, x, y, z, q, Ex, Ey, Ez; at_cathode::Bool = false
                    Ex, Ey, Ez))
 end
 
+"""
+    step_host!(mesh, x, y, z, q, Ex, Ey, Ez; at_cathode=false, wait=true)
+
+The same step with HOST arrays (`Array{P}`, ideally pinned with `CUDA.pin`): uploads, deposits, solves, interpolates and
+downloads in overlapping chunks (scb_step_host).  With `wait=false` the call returns as soon as everything is queued
+(scb_step_host_async): up to two steps may be in flight, the upload of one overlapping the download of the previous one;
+consecutive steps need distinct output arrays, and `step_host_wait!(mesh)` must return before any of the arrays is
+touched.
+"""
+function step_host!(mesh::Mesh3D{T}, x::Array{P}, y::Array{P}, z::Array{P}, q::Array{P}, Ex::Array{P}, Ey::Array{P},
+                    Ez::Array{P}; at_cathode::Bool = false, wait::Bool = true) where {T,P}
+    h = handle(mesh)
+    args = (h.ptr, length(x), pointer(x), pointer(y), pointer(z), pointer(q), dtag(P), mesh.rho, mesh.efield, dtag(T),
+            _n(mesh), _f3(mesh.min_bounds), _f3(mesh.max_bounds), _f3(mesh.delta), Float64(mesh.gamma),
+            at_cathode ? 1 : 0, pointer(Ex), pointer(Ey), pointer(Ez))
+    sig = (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint,
+           Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid})
+    GC.@preserve x y z q Ex Ey Ez begin
+        if wait
+            check(h, ccall((:scb_step_host, LIB), Cint, sig, args...))
+        else
+            check(h, ccall((:scb_step_host_async, LIB), Cint, sig, args...))
+        end
+    end
+end
+
+step_host_wait!(mesh::Mesh3D) = (h = handle(mesh); check(h, ccall((:scb_step_host_wait, LIB), Cint, (Ptr{Cvoid},), h.ptr)))
+
 end # module SpaceChargeB200
