@@ -158,6 +158,51 @@ SCB_API int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, co
              const double min_bounds[3], const double max_bounds[3], const double delta[3],
              double gamma, int at_cathode, void* ex, void* ey, void* ez);
 
+/* ---- extension: strided / array-of-structures particle layouts ------------ */
+/* The reference takes four separate dense vectors (src/deposition.jl:218-223,
+ * src/interpolation.jl:100-104).  Tracking codes such as Bmad keep one record per particle (the
+ * phase-space vector (x, px, y, py, z, pz) plus charge and bookkeeping), so handing the reference
+ * dense vectors costs a de-interleaving pass over the whole bunch before and after every step.
+ * The *_strided entry points read and write such records in place: every array is a base pointer
+ * plus an ELEMENT stride (in units of the pdt element, not bytes), particle i of array a lives at
+ * a[i * stride_a].  All strides 1 = the dense calls above (same kernels, same results).
+ *   x, y, z     >= 1
+ *   q           >= 0; 0 = every particle carries the charge q[0] (equal-weight macro-particles:
+ *               saves reading Np charges)
+ *   ex, ey, ez  >= 1 (interpolated field, or the momenta updated by the fused kick); output
+ *               elements of different particles must not alias.
+ * Example, Bmad-style phase-space records `double vec[6]` in an array `v` of Np records, charges
+ * in a dense vector: x = v, y = v + 2, z = v + 4 with strides 6; the kick updates px = v + 1,
+ * py = v + 3, pz = v + 5 with strides 6 -- the bunch is never copied.
+ * Arithmetic, clamping and error codes are those of the dense calls. */
+typedef struct scb_particle_strides {
+    int64_t x, y, z, q;        /* inputs (q is ignored by the calls that take no charges)          */
+    int64_t ex, ey, ez;        /* outputs (ignored by scb_deposit_strided / scb_bounds_strided)    */
+    int64_t reserved;
+} scb_particle_strides;
+
+SCB_API int scb_deposit_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                                const void* q, const scb_particle_strides* st, int pdt, void* rho, int mdt,
+                                const int64_t n[3], const double min_bounds[3], const double delta[3],
+                                int clear);
+SCB_API int scb_interpolate_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                                    const scb_particle_strides* st, int pdt, const void* efield, int mdt,
+                                    const int64_t n[3], const double min_bounds[3], const double delta[3],
+                                    void* ex, void* ey, void* ez);
+SCB_API int scb_interpolate_kick_strided(scb_handle* h, int64_t np, const void* x, const void* y,
+                                         const void* z, const scb_particle_strides* st, int pdt,
+                                         const void* efield, int mdt, const int64_t n[3],
+                                         const double min_bounds[3], const double delta[3], void* px,
+                                         void* py, void* pz, double coef_xy, double coef_z);
+SCB_API int scb_bounds_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                               const scb_particle_strides* st, int pdt, double out_min[3],
+                               double out_max[3]);
+SCB_API int scb_step_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                             const void* q, const scb_particle_strides* st, int pdt, void* rho,
+                             void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                             const double max_bounds[3], const double delta[3], double gamma,
+                             int at_cathode, void* ex, void* ey, void* ez);
+
 /* ---- the same step with HOST particle buffers (pinned or pageable) ------------------------ */
 /* Copies x,y,z,q host->device in chunks overlapped with deposition, solves, interpolates in
  * chunks overlapped with the device->host copy of ex,ey,ez.  rho/efield stay on the device

@@ -177,6 +177,24 @@ def _device_array(a, device):
     return t.contiguous().view(-1)
 
 
+def _particle_view(a, device, allow_broadcast=False):
+    """Particle array -> (CUDA tensor, element stride) WITHOUT copying when ``a`` is a 1-D CUDA tensor
+    view with a positive stride -- e.g. ``records[:, 0]`` of an (Np, 6) phase-space array, the layout of
+    Bmad-style callers.  ``allow_broadcast``: a stride-0 view (``q0.expand(Np)``) means
+    one charge for every particle.  Anything else goes through ``_device_array`` (dense copy, stride 1)."""
+    torch = _torch()
+    if (isinstance(a, torch.Tensor) and a.device.type == "cuda" and a.dim() == 1 and a.numel() > 0
+            and a.dtype in (torch.float32, torch.float64)):
+        st = a.stride(0)
+        if st >= 1 or (allow_broadcast and st == 0):
+            return a, int(st)
+    return _device_array(a, device), 1
+
+
+def _strides(x=1, y=1, z=1, q=1, ex=1, ey=1, ez=1):
+    return _lib.scb_particle_strides(x, y, z, q, ex, ey, ez, 0)
+
+
 def _extrema_host(a):
     arr = np.asarray(a)
     if arr.dtype.kind != "f" or arr.dtype.itemsize not in (4, 8):
@@ -268,11 +286,15 @@ class Mesh3D:
         if all(isinstance(p, torch.Tensor) and p.device.type == "cuda" for p in (px, py, pz)):
             hd = handle if handle is not None else default_handle(px.device.index)
             hd.use_current_stream()
-            x, y, z = (p.contiguous().view(-1) for p in (px, py, pz))
+            (x, sx), (y, sy), (z, sz) = (_particle_view(p, px.device.index) for p in (px, py, pz))
             if not (x.dtype == y.dtype == z.dtype):
                 raise ErrorException("particle coordinate arrays must share one element type")
             omin, omax = _lib.f64x3((0, 0, 0)), _lib.f64x3((0, 0, 0))
-            hd.check(hd.lib.scb_bounds(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype), omin, omax))
+            if sx == sy == sz == 1:
+                hd.check(hd.lib.scb_bounds(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype), omin, omax))
+            else:
+                hd.check(hd.lib.scb_bounds_strided(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                                                   C.byref(_strides(sx, sy, sz)), _tag(x.dtype), omin, omax))
             P = np.float32 if x.dtype == torch.float32 else np.float64
             ext = [(P(omin[a]), P(omax[a]), P) for a in range(3)]
         else:
@@ -376,11 +398,17 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
         raise ErrorException("Particle coordinate and charge arrays must have the same length.")
     hd = mesh.handle
     hd.use_current_stream()
-    x, y, z, q = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z, particles_q))
+    (x, sx), (y, sy), (z, sz) = (_particle_view(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    q, sq = _particle_view(particles_q, mesh.device, allow_broadcast=True)
     if not (x.dtype == y.dtype == z.dtype == q.dtype):
         raise ErrorException("particle arrays must share one element type")
-    hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
-                                mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
+    if sx == sy == sz == sq == 1:
+        hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
+                                    mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
+    else:   # strided views (AoS records, broadcast charge): read in place, no dense copy
+        hd.check(hd.lib.scb_deposit_strided(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(),
+                                            C.byref(_strides(sx, sy, sz, sq)), _tag(x.dtype), mesh._rho.data_ptr(),
+                                            mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
     if mesh.group is not None and not mesh.sharded:
         from .sharding import allreduce_rho
         allreduce_rho(mesh._rho, mesh.group)
@@ -432,17 +460,24 @@ def interpolate_kick_(mesh: Mesh3D, particles_x, particles_y, particles_z, px, p
     tensors of the particles' element type, updated in place."""
     hd = mesh.handle
     hd.use_current_stream()
-    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    (x, sx), (y, sy), (z, sz) = (_particle_view(a, mesh.device) for a in (particles_x, particles_y, particles_z))
     if not (x.dtype == y.dtype == z.dtype == px.dtype == py.dtype == pz.dtype):
         raise ErrorException("particle arrays must share one element type")
     if not (x.numel() == px.numel() == py.numel() == pz.numel()):
         raise ErrorException("Particle coordinate and momentum arrays must have the same length.")
     for p in (px, py, pz):
-        if p.device.type != "cuda" or not p.is_contiguous():
-            raise ErrorException("momentum arrays must be contiguous CUDA tensors (they are updated in place)")
-    hd.check(hd.lib.scb_interpolate_kick(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
-                                         mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
-                                         px.data_ptr(), py.data_ptr(), pz.data_ptr(), float(coef_xy), float(coef_z)))
+        if p.device.type != "cuda" or p.dim() != 1 or (p.numel() > 1 and p.stride(0) < 1):
+            raise ErrorException("momentum arrays must be 1-D CUDA tensors or positive-stride views (they are updated in place)")
+    so = [p.stride(0) if p.numel() > 1 else 1 for p in (px, py, pz)]
+    if sx == sy == sz == 1 and so == [1, 1, 1]:
+        hd.check(hd.lib.scb_interpolate_kick(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                             mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                             px.data_ptr(), py.data_ptr(), pz.data_ptr(), float(coef_xy), float(coef_z)))
+    else:
+        hd.check(hd.lib.scb_interpolate_kick_strided(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                                                     C.byref(_strides(sx, sy, sz, 1, *so)), _tag(x.dtype),
+                                                     mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                                     px.data_ptr(), py.data_ptr(), pz.data_ptr(), float(coef_xy), float(coef_z)))
 
 
 def solve_freespace_(mesh: Mesh3D, offset=(0.0, 0.0, 0.0)) -> None:
@@ -461,13 +496,19 @@ def interpolate_field(mesh: Mesh3D, particles_x, particles_y, particles_z):
     torch = _torch()
     hd = mesh.handle
     hd.use_current_stream()
-    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    (x, sx), (y, sy), (z, sz) = (_particle_view(a, mesh.device) for a in (particles_x, particles_y, particles_z))
     if not (x.dtype == y.dtype == z.dtype):
         raise ErrorException("particle arrays must share one element type")
-    ex, ey, ez = (torch.empty_like(x) for _ in range(3))
-    hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
-                                    mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
-                                    ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+    ex, ey, ez = (torch.empty(x.numel(), dtype=x.dtype, device=x.device) for _ in range(3))
+    if sx == sy == sz == 1:
+        hd.check(hd.lib.scb_interpolate(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                        mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                        ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+    else:
+        hd.check(hd.lib.scb_interpolate_strided(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                                                C.byref(_strides(sx, sy, sz)), _tag(x.dtype), mesh._efield.data_ptr(),
+                                                mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(),
+                                                ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
     return ex, ey, ez
 
 
@@ -503,6 +544,17 @@ def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> Non
     (the timed body of benchmark/full_pipeline_benchmark.jl:26-30, without the per-call allocation)."""
     hd = mesh.handle
     hd.use_current_stream()
+    st = [t.stride(0) if t.numel() > 1 else 1 for t in (x, y, z, q, ex, ey, ez)]
+    if st != [1] * 7:
+        if mesh.group is not None:
+            raise ErrorException("strided particle views are single-GPU; pass dense shards to a particle-sharded step_")
+        if min(st[:3] + st[4:]) < 1 or st[3] < 0:
+            raise ErrorException("particle views need positive strides (the charge may be a stride-0 broadcast)")
+        hd.check(hd.lib.scb_step_strided(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(),
+                                         C.byref(_strides(*st)), _tag(x.dtype), mesh._rho.data_ptr(),
+                                         mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(),
+                                         float(mesh.gamma), 1 if at_cathode else 0, ex.data_ptr(), ey.data_ptr(), ez.data_ptr()))
+        return
     if mesh.group is None:
         hd.check(hd.lib.scb_step(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
                                  mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(),

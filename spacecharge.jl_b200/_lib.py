@@ -39,9 +39,16 @@ class scb_timing(C.Structure):
                 ("green_ms", C.c_float), ("pass_ms", C.c_float * 8)]
 
 
+class scb_particle_strides(C.Structure):
+    """Element strides of strided / AoS particle arrays (include/spacecharge_b200.h)."""
+    _fields_ = [("x", C.c_int64), ("y", C.c_int64), ("z", C.c_int64), ("q", C.c_int64),
+                ("ex", C.c_int64), ("ey", C.c_int64), ("ez", C.c_int64), ("reserved", C.c_int64)]
+
+
 _I64x3 = C.c_int64 * 3
 _F64x3 = C.c_double * 3
 _vp = C.c_void_p
+_PST = C.POINTER(scb_particle_strides)
 
 # name -> (restype, argtypes); must list every symbol include/spacecharge_b200.h declares
 SIGNATURES = {
@@ -68,6 +75,15 @@ SIGNATURES = {
     "scb_cell_index": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int, _F64x3, _F64x3, _vp, _vp, _vp]),
     "scb_step": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _F64x3,
                            C.c_double, C.c_int, _vp, _vp, _vp]),
+    "scb_deposit_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _PST, C.c_int, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
+                                      C.c_int]),
+    "scb_interpolate_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _PST, C.c_int, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
+                                          _vp, _vp, _vp]),
+    "scb_interpolate_kick_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _PST, C.c_int, _vp, C.c_int, _I64x3, _F64x3,
+                                               _F64x3, _vp, _vp, _vp, C.c_double, C.c_double]),
+    "scb_bounds_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _PST, C.c_int, _F64x3, _F64x3]),
+    "scb_step_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _PST, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3,
+                                   _F64x3, _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
     "scb_step_host": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
                                 _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
     "scb_step_host_async": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3,

@@ -257,7 +257,7 @@ int ensure_packed(scb_handle* h, size_t bytes) {
 // deposit: cell-tile accumulation when there are enough particles to pay for zeroing and folding the
 // tiles (deposit_mode 0 = auto, 1 = one thread per particle, 2 = lane pairs, 3 = tiles)
 int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
-                void* rho, int mdt, const Geom3& g, bool clear, bool cleared_already) {
+                void* rho, int mdt, const Geom3& g, bool clear, bool cleared_already, const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     int mode = h->opt.deposit_mode;
     if (mode == 0) mode = np >= ng ? 3 : 2;
@@ -271,23 +271,24 @@ int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const v
     }
     if (mode == 3) {
         // a cleared rho equals "overwrite"; an un-cleared one is accumulated into
-        SCB_CUDA(h, launch_deposit_tiles(pdt, mdt, np, x, y, z, q, h->tiles, rho, g, clear ? 0 : 1, h->stream));
+        SCB_CUDA(h, launch_deposit_tiles(pdt, mdt, np, x, y, z, q, h->tiles, rho, g, clear ? 0 : 1, h->stream, lay));
         h->launches += 2;
         return SCB_OK;
     }
     if (clear && !cleared_already) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)ng * dt_size(mdt), h->stream));
-    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, g, mode, h->stream));
+    SCB_CUDA(h, launch_deposit(pdt, mdt, np, x, y, z, q, rho, g, mode, h->stream, lay));
     if (np > 0) h->launches += 1;
     return SCB_OK;
 }
 
 // gather: repack the field node-major when there are enough particles to pay for the extra pass
 int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, const void* efield,
-                    int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready, const Kick& kick = Kick()) {
+                    int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready, const Kick& kick = Kick(),
+                    const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     const bool use_packed = (packed_ready && *packed_ready) || np * 4 >= ng;
     if (!use_packed) {
-        SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick));
+        SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick, lay));
         h->launches += 1;
         return SCB_OK;
     }
@@ -297,7 +298,7 @@ int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
         h->launches += 1;
         if (packed_ready) *packed_ready = true;
     }
-    SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream, kick));
+    SCB_CUDA(h, launch_interpolate_packed(pdt, mdt, np, x, y, z, h->packed, g, ex, ey, ez, h->stream, kick, lay));
     h->launches += 1;
     return SCB_OK;
 }
@@ -1178,6 +1179,109 @@ int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, const void
     SCB_TRY(scb_deposit(h, np, x, y, z, q, pdt, rho, mdt, n, min_bounds, delta, 1));
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     return scb_interpolate(h, np, x, y, z, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
+}
+
+// ---- strided / AoS particle layouts ------------------------------------------
+namespace {
+// element strides from the C struct; `need_q` / `need_out`: which members the call reads
+int layout_from(scb_handle* h, const scb_particle_strides* st, bool need_q, bool need_out, PLayout* L) {
+    if (!st) return fail(h, SCB_ERR_INVALID_ARG, "null strides");
+    if (st->x < 1 || st->y < 1 || st->z < 1) return fail(h, SCB_ERR_INVALID_ARG, "coordinate strides must be >= 1");
+    if (need_q && st->q < 0) return fail(h, SCB_ERR_INVALID_ARG, "charge stride must be >= 0 (0 = one charge for all particles)");
+    if (need_out && (st->ex < 1 || st->ey < 1 || st->ez < 1)) return fail(h, SCB_ERR_INVALID_ARG, "output strides must be >= 1");
+    L->x = st->x; L->y = st->y; L->z = st->z;
+    L->q = need_q ? st->q : 1;
+    if (need_out) { L->ex = st->ex; L->ey = st->ey; L->ez = st->ez; }
+    return SCB_OK;
+}
+}  // namespace
+
+int scb_deposit_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q,
+                        const scb_particle_strides* st, int pdt, void* rho, int mdt, const int64_t n[3],
+                        const double min_bounds[3], const double delta[3], int clear) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !rho || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_deposit_strided");
+    if (np > 0 && (!x || !y || !z || !q)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    PLayout L;
+    SCB_TRY(layout_from(h, st, true, false, &L));
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    tick(h, 0);
+    SCB_TRY(run_deposit(h, np, x, y, z, q, pdt, rho, mdt, make_geom(n, min_bounds, delta), clear != 0, false, &L));
+    tick(h, 1);
+    h->t_dep = true;
+    return SCB_OK;
+}
+
+int scb_interpolate_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                            const scb_particle_strides* st, int pdt, const void* efield, int mdt, const int64_t n[3],
+                            const double min_bounds[3], const double delta[3], void* ex, void* ey, void* ez) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !efield || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_interpolate_strided");
+    if (np > 0 && (!x || !y || !z || !ex || !ey || !ez)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    PLayout L;
+    SCB_TRY(layout_from(h, st, false, true, &L));
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    tick(h, 4);
+    if (np > 0) SCB_TRY(run_interpolate(h, np, x, y, z, pdt, efield, mdt, make_geom(n, min_bounds, delta), ex, ey, ez, nullptr, Kick(), &L));
+    tick(h, 5);
+    h->t_interp = true;
+    return SCB_OK;
+}
+
+int scb_interpolate_kick_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                                 const scb_particle_strides* st, int pdt, const void* efield, int mdt,
+                                 const int64_t n[3], const double min_bounds[3], const double delta[3], void* px,
+                                 void* py, void* pz, double coef_xy, double coef_z) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !efield || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_interpolate_kick_strided");
+    if (np > 0 && (!x || !y || !z || !px || !py || !pz)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    PLayout L;
+    SCB_TRY(layout_from(h, st, false, true, &L));
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    Kick k;
+    k.on = 1;
+    k.cxy = coef_xy;
+    k.cz = coef_z;
+    tick(h, 4);
+    if (np > 0) SCB_TRY(run_interpolate(h, np, x, y, z, pdt, efield, mdt, make_geom(n, min_bounds, delta), px, py, pz, nullptr, k, &L));
+    tick(h, 5);
+    h->t_interp = true;
+    return SCB_OK;
+}
+
+int scb_bounds_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                       const scb_particle_strides* st, int pdt, double out_min[3], double out_max[3]) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np <= 0) return fail(h, SCB_ERR_INVALID_ARG, "Particle arrays cannot be empty.");
+    if (!x || !y || !z || !out_min || !out_max || !valid_dt(pdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_bounds_strided");
+    PLayout L;
+    SCB_TRY(layout_from(h, st, false, false, &L));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_CUDA(h, launch_bounds(pdt, np, x, y, z, reinterpret_cast<double*>(h->d_bounds), h->stream, &L));
+    h->launches += 2;
+    unsigned long long host[6];
+    SCB_CUDA(h, cudaMemcpyAsync(host, h->d_bounds, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < 3; ++a) {
+        out_min[a] = key_to_double(host[a]);
+        out_max[a] = key_to_double(host[3 + a]);
+    }
+    return SCB_OK;
+}
+
+int scb_step_strided(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q,
+                     const scb_particle_strides* st, int pdt, void* rho, void* efield, int mdt, const int64_t n[3],
+                     const double min_bounds[3], const double max_bounds[3], const double delta[3], double gamma,
+                     int at_cathode, void* ex, void* ey, void* ez) {
+    SCB_TRY(scb_deposit_strided(h, np, x, y, z, q, st, pdt, rho, mdt, n, min_bounds, delta, 1));
+    SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    return scb_interpolate_strided(h, np, x, y, z, st, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
 }
 
 int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,

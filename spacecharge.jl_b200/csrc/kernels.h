@@ -34,6 +34,13 @@ struct Kick {
     double cxy = 0.0, cz = 0.0;   // p_{x,y} += cxy * E_{x,y},  p_z += cz * E_z
 };
 
+// element strides of the caller's particle arrays (scb_*_strided entry points, SURVEY.md 8(f)-3: AoS / strided
+// layouts of Bmad-style callers); contiguous = all 1.  q = 0 means one charge shared by every particle.
+struct PLayout {
+    long long x = 1, y = 1, z = 1, q = 1;   // inputs
+    long long ex = 1, ey = 1, ez = 1;       // outputs (interpolated field, or the momenta of the fused kick)
+};
+
 // green.cu
 cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStream_t s);
 cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s);
@@ -48,14 +55,16 @@ cudaError_t launch_green_convert_full(void* G, int dt_f64, const double2* spec, 
 // particles.cu  (pdt/mdt: 0 = f32, 1 = f64)
 // mode 1: one thread per particle; otherwise two lanes per particle (x-neighbours coalesce in L2)
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s);
+                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s,
+                           const PLayout* lay = nullptr);
 // cell-tile deposit: `tiles` = 4 * Ng mesh elements of scratch; zeroes it, accumulates, folds into rho
 // (rho is overwritten, or added to when accumulate != 0)
 cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s);
+                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s,
+                                 const PLayout* lay = nullptr);
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
-                               const Kick& kick = Kick());
+                               const Kick& kick = Kick(), const PLayout* lay = nullptr);
 // node-major repack of efield (32 bytes per node) and the gather that reads it
 size_t packed_bytes_per_node(int mdt);   // node-major record size
 int interp_mode();   // SCB_INTERP_MODE: 0 = default gather kernels
@@ -63,12 +72,12 @@ cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const 
                                long long first_node = 0, long long count = -1);
 cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                       const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
-                                      const Kick& kick = Kick());
+                                      const Kick& kick = Kick(), const PLayout* lay = nullptr);
 cudaError_t launch_bfield(int mdt, const void* efield, void* bfield, long long ng, double beta_over_c, cudaStream_t s);
 cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                               const Geom3& g, long long* ix, long long* iy, long long* iz, cudaStream_t s);
 // partial[0..2] = min, partial[3..5] = max as doubles; must be initialised by the launcher
 cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z,
-                          double* out6, cudaStream_t s);
+                          double* out6, cudaStream_t s, const PLayout* lay = nullptr);
 
 }  // namespace scb

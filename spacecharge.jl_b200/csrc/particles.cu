@@ -35,6 +35,10 @@ __device__ __forceinline__ void red_add_hint(float* a, float v, unsigned long lo
     asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
 }
 
+// index of particle i in an array with element stride s; ST = false (contiguous callers) compiles to i itself, so the
+// tuned kernels are unchanged for the reference's SoA layout
+template <bool ST> __device__ __forceinline__ long long pidx(long long i, long long s) { return ST ? i * s : i; }
+
 template <typename W> struct CellW {
     int i[3];
     W f[3];
@@ -99,10 +103,10 @@ __global__ void __launch_bounds__(256) k_deposit(long long np, const P* __restri
 // ((q*wx)*wy)*wz, so the per-contribution values are bit-identical to k_deposit; only the (already
 // unordered) accumulation order differs.  (An eight-lanes-per-particle version had the same
 // sector count but spent a third of the LSU pipe on shuffles.)
-template <typename P, typename T>
+template <typename P, typename T, bool ST>
 __global__ void __launch_bounds__(256) k_deposit_pair(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                        const P* __restrict__ z, const P* __restrict__ q,
-                                                       T* __restrict__ rho, const Geom3 g) {
+                                                       T* __restrict__ rho, const Geom3 g, const PLayout L) {
     using W = typename promote<P, T>::type;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -116,8 +120,9 @@ __global__ void __launch_bounds__(256) k_deposit_pair(long long np, const P* __r
         long long off = 0;
         if (i < np) {
             CellW<W> c;
-            locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
-            charge = (W)ld_stream(q + i);
+            locate<W>((W)ld_stream(x + pidx<ST>(i, L.x)), (W)ld_stream(y + pidx<ST>(i, L.y)),
+                      (W)ld_stream(z + pidx<ST>(i, L.z)), g, c);
+            charge = (W)ld_stream(q + pidx<ST>(i, L.q));
             f0 = c.f[0]; f1 = c.f[1]; f2 = c.f[2];
             off = c.i[0] + sy * c.i[1] + sz * c.i[2];
         }
@@ -152,10 +157,10 @@ __global__ void __launch_bounds__(256) k_deposit_pair(long long np, const P* __r
 // two reduction instructions (plane iz, plane iz+1): 2 sector transactions per particle.  A second
 // kernel folds the tiles into rho: node (i,j,k) = T(i,j,k)[0] + T(i-1,j,k)[1] + T(i,j-1,k)[2] +
 // T(i-1,j-1,k)[3] (fixed order).  Per-contribution values are the reference's ((q*wx)*wy)*wz.
-template <typename P, typename T>
+template <typename P, typename T, bool ST>
 __global__ void __launch_bounds__(256) k_deposit_tiles(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                         const P* __restrict__ z, const P* __restrict__ q,
-                                                        T* __restrict__ tiles, const Geom3 g) {
+                                                        T* __restrict__ tiles, const Geom3 g, const PLayout L) {
     using W = typename promote<P, T>::type;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -169,13 +174,17 @@ __global__ void __launch_bounds__(256) k_deposit_tiles(long long np, const P* __
     P px = 0, py = 0, pz = 0, pq = 0;
     if (warp * 32 + lane < np) {
         const long long i0 = warp * 32 + lane;
-        px = ld_stream(x + i0); py = ld_stream(y + i0); pz = ld_stream(z + i0); pq = ld_stream(q + i0);
+        px = ld_stream(x + pidx<ST>(i0, L.x)); py = ld_stream(y + pidx<ST>(i0, L.y));
+        pz = ld_stream(z + pidx<ST>(i0, L.z)); pq = ld_stream(q + pidx<ST>(i0, L.q));
     }
     for (long long base = warp * 32; base < np; base += nwarps * 32) {
         const long long i = base + lane;
         const long long inext = i + nwarps * 32;
         P nx_ = 0, ny_ = 0, nz_ = 0, nq_ = 0;
-        if (inext < np) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); nz_ = ld_stream(z + inext); nq_ = ld_stream(q + inext); }
+        if (inext < np) {
+            nx_ = ld_stream(x + pidx<ST>(inext, L.x)); ny_ = ld_stream(y + pidx<ST>(inext, L.y));
+            nz_ = ld_stream(z + pidx<ST>(inext, L.z)); nq_ = ld_stream(q + pidx<ST>(inext, L.q));
+        }
         W f0 = 0, f1 = 0, f2 = 0, charge = 0;
         long long off = 0;
         if (i < np) {
@@ -228,17 +237,18 @@ __device__ __forceinline__ void put_result(P* __restrict__ arr, long long i, W v
 }
 
 // ---- interpolate: one thread per particle, 24 gathers --------------------------------------
-template <typename P, typename T>
+template <typename P, typename T, bool ST>
 __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                       const P* __restrict__ z, const T* __restrict__ e,
                                                       const Geom3 g, P* __restrict__ ex, P* __restrict__ ey,
-                                                      P* __restrict__ ez, const Kick kick) {
+                                                      P* __restrict__ ez, const Kick kick, const PLayout L) {
     using W = typename promote<P, T>::type;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1], sc = sz * g.n[2];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
         CellW<W> c;
-        locate<W>((W)ld_stream(x + i), (W)ld_stream(y + i), (W)ld_stream(z + i), g, c);
+        locate<W>((W)ld_stream(x + pidx<ST>(i, L.x)), (W)ld_stream(y + pidx<ST>(i, L.y)),
+                  (W)ld_stream(z + pidx<ST>(i, L.z)), g, c);
         const W dx = c.f[0], dy = c.f[1], dz = c.f[2];
         const W one = (W)1;
         // src/interpolation.jl:46-53
@@ -260,9 +270,9 @@ __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __re
                      (W)__ldg(bk + sy + 1) * w110 + (W)__ldg(bk + sz) * w001 + (W)__ldg(bk + sz + 1) * w101 +
                      (W)__ldg(bk + sz + sy) * w011 + (W)__ldg(bk + sz + sy + 1) * w111;
         }
-        put_result<P, W>(ex, i, out[0], kick, false);
-        put_result<P, W>(ey, i, out[1], kick, false);
-        put_result<P, W>(ez, i, out[2], kick, true);
+        put_result<P, W>(ex, pidx<ST>(i, L.ex), out[0], kick, false);
+        put_result<P, W>(ey, pidx<ST>(i, L.ey), out[1], kick, false);
+        put_result<P, W>(ez, pidx<ST>(i, L.ez), out[2], kick, true);
     }
 }
 
@@ -421,12 +431,12 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
 // themselves (same address: one wavefront per 16 particles and array), locate it redundantly, and the even lane
 // stores the result (16 active lanes, one 128-byte line): 12 shuffle wavefronts per 32 particles remain (the x0 + x1
 // halves of the three components).  Same arithmetic, bit-identical results.
-template <typename P>
+template <typename P, bool ST>
 __global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
                                                                 const P* __restrict__ y, const P* __restrict__ z,
                                                                 const double4* __restrict__ e, const Geom3 g,
                                                                 P* __restrict__ ex, P* __restrict__ ey,
-                                                                P* __restrict__ ez, const Kick kick) {
+                                                                P* __restrict__ ez, const Kick kick, const PLayout L) {
     using W = double;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -443,20 +453,20 @@ __global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, con
     const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
     if (i < np) {
-        cz = ld_stream(z + i);
-        if (!zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+        cz = ld_stream(z + pidx<ST>(i, L.z));
+        if (!zfirst) { cx = ld_stream(x + pidx<ST>(i, L.x)); cy = ld_stream(y + pidx<ST>(i, L.y)); }
     }
     for (; __any_sync(FULL, i < np); i += nwarps * 16) {
         const long long inext = i + nwarps * 16;
         P nx_ = 0, ny_ = 0, nz_ = 0;
         if (inext < np) {
-            nz_ = ld_stream(z + inext);
-            if (!zfirst) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); }
+            nz_ = ld_stream(z + pidx<ST>(inext, L.z));
+            if (!zfirst) { nx_ = ld_stream(x + pidx<ST>(inext, L.x)); ny_ = ld_stream(y + pidx<ST>(inext, L.y)); }
         }
         const bool live = i < np && (!filt || z_selected<W>((W)cz, g));
         W acc[3] = {0, 0, 0};
         if (live) {
-            if (zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+            if (zfirst) { cx = ld_stream(x + pidx<ST>(i, L.x)); cy = ld_stream(y + pidx<ST>(i, L.y)); }
             CellW<W> c;
             locate<W>((W)cx, (W)cy, (W)cz, g, c);
             const double4* b = e + (c.i[0] + sy * c.i[1] + sz * c.i[2]) + kx;
@@ -480,20 +490,20 @@ __global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, con
             acc[k] = kx ? other + acc[k] : acc[k] + other;   // x0 part + x1 part
         }
         if (live && kx == 0) {
-            put_result<P, W>(ex, i, acc[0], kick, false);
-            put_result<P, W>(ey, i, acc[1], kick, false);
-            put_result<P, W>(ez, i, acc[2], kick, true);
+            put_result<P, W>(ex, pidx<ST>(i, L.ex), acc[0], kick, false);
+            put_result<P, W>(ey, pidx<ST>(i, L.ey), acc[1], kick, false);
+            put_result<P, W>(ez, pidx<ST>(i, L.ez), acc[2], kick, true);
         }
         cx = nx_; cy = ny_; cz = nz_;
     }
 }
 
-template <typename P>
+template <typename P, bool ST>
 __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, const P* __restrict__ x,
                                                                  const P* __restrict__ y, const P* __restrict__ z,
                                                                  const float4* __restrict__ e, const Geom3 g,
                                                                  P* __restrict__ ex, P* __restrict__ ey,
-                                                                 P* __restrict__ ez, const Kick kick) {
+                                                                 P* __restrict__ ez, const Kick kick, const PLayout L) {
     using W = typename promote<P, float>::type;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
@@ -504,21 +514,21 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
     const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
     if (i < np) {
-        cz = ld_stream(z + i);
-        if (!zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+        cz = ld_stream(z + pidx<ST>(i, L.z));
+        if (!zfirst) { cx = ld_stream(x + pidx<ST>(i, L.x)); cy = ld_stream(y + pidx<ST>(i, L.y)); }
     }
     for (; i < np; i += stride) {
         const long long inext = i + stride;
         P nx_ = 0, ny_ = 0, nz_ = 0;
         if (inext < np) {
-            nz_ = ld_stream(z + inext);
-            if (!zfirst) { nx_ = ld_stream(x + inext); ny_ = ld_stream(y + inext); }
+            nz_ = ld_stream(z + pidx<ST>(inext, L.z));
+            if (!zfirst) { nx_ = ld_stream(x + pidx<ST>(inext, L.x)); ny_ = ld_stream(y + pidx<ST>(inext, L.y)); }
         }
         if (filt && !z_selected<W>((W)cz, g)) {
             cx = nx_; cy = ny_; cz = nz_;
             continue;
         }
-        if (zfirst) { cx = ld_stream(x + i); cy = ld_stream(y + i); }
+        if (zfirst) { cx = ld_stream(x + pidx<ST>(i, L.x)); cy = ld_stream(y + pidx<ST>(i, L.y)); }
         CellW<W> c;
         locate<W>((W)cx, (W)cy, (W)cz, g, c);
         const float4* b = e + 2 * (c.i[0] + sy * c.i[1] + sz * c.i[2]);
@@ -541,9 +551,9 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
         for (int k = 0; k < 3; ++k)
             out[k] = (W)p00[k] * w000 + (W)p00[4 + k] * w100 + (W)p10[k] * w010 + (W)p10[4 + k] * w110 +
                      (W)p01[k] * w001 + (W)p01[4 + k] * w101 + (W)p11[k] * w011 + (W)p11[4 + k] * w111;
-        put_result<P, W>(ex, i, out[0], kick, false);
-        put_result<P, W>(ey, i, out[1], kick, false);
-        put_result<P, W>(ez, i, out[2], kick, true);
+        put_result<P, W>(ex, pidx<ST>(i, L.ex), out[0], kick, false);
+        put_result<P, W>(ey, pidx<ST>(i, L.ey), out[1], kick, false);
+        put_result<P, W>(ez, pidx<ST>(i, L.ez), out[2], kick, true);
         cx = nx_; cy = ny_; cz = nz_;
     }
 }
@@ -584,19 +594,21 @@ __global__ void k_bounds_init(unsigned long long* out6) {
     else if (threadIdx.x < 6) out6[threadIdx.x] = 0ull;
 }
 
-template <typename P>
+template <typename P, bool ST>
 __global__ void __launch_bounds__(256) k_bounds(long long np, const P* __restrict__ x, const P* __restrict__ y,
-                                                 const P* __restrict__ z, unsigned long long* __restrict__ out6) {
+                                                 const P* __restrict__ z, unsigned long long* __restrict__ out6,
+                                                 const PLayout L) {
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     const long long stride = (long long)gridDim.x * blockDim.x;
     const P* arr[3] = {x, y, z};
+    const long long es[3] = {L.x, L.y, L.z};
     // four independent streaming loads per array and iteration keep enough bytes in flight for HBM
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < np; i += 4 * stride) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double v0 = (double)ld_stream(arr[a] + i), v1 = (double)ld_stream(arr[a] + i + stride);
-            const double v2 = (double)ld_stream(arr[a] + i + 2 * stride), v3 = (double)ld_stream(arr[a] + i + 3 * stride);
+            const double v0 = (double)ld_stream(arr[a] + pidx<ST>(i, es[a])), v1 = (double)ld_stream(arr[a] + pidx<ST>(i + stride, es[a]));
+            const double v2 = (double)ld_stream(arr[a] + pidx<ST>(i + 2 * stride, es[a])), v3 = (double)ld_stream(arr[a] + pidx<ST>(i + 3 * stride, es[a]));
             lo[a] = fmin(fmin(lo[a], fmin(v0, v1)), fmin(v2, v3));
             hi[a] = fmax(fmax(hi[a], fmax(v0, v1)), fmax(v2, v3));
         }
@@ -604,7 +616,7 @@ __global__ void __launch_bounds__(256) k_bounds(long long np, const P* __restric
     for (; i < np; i += stride) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double v = (double)ld_stream(arr[a] + i);
+            const double v = (double)ld_stream(arr[a] + pidx<ST>(i, es[a]));
             lo[a] = fmin(lo[a], v);
             hi[a] = fmax(hi[a], v);
         }
@@ -642,16 +654,21 @@ static inline unsigned particle_grid(long long np, int bs, int per_sm) {
     else if (pdt == 1 && mdt == 0) { CALL(double, float) }                     \
     else { CALL(double, double) }
 
+// ST = true instantiations serve the scb_*_strided entry points; contiguous callers keep the ST = false kernels
+#define SCB_LAYOUT(...)                                                        \
+    if (lay) { const PLayout L = *lay; constexpr bool ST = true; __VA_ARGS__ } \
+    else { const PLayout L{}; constexpr bool ST = false; __VA_ARGS__ }
+
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s) {
+                           const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
-    if (mode == 1) {
+    if (mode == 1 && !lay) {
 #define CALL(P, T) k_deposit<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
         SCB_DISPATCH_PT(CALL)
 #undef CALL
     } else {
-#define CALL(P, T) k_deposit_pair<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
+#define CALL(P, T) SCB_LAYOUT(k_deposit_pair<P, T, ST><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g, L);)
         SCB_DISPATCH_PT(CALL)
 #undef CALL
     }
@@ -660,23 +677,24 @@ cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const 
 
 cudaError_t launch_interpolate(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
-                               const Kick& kick) {
+                               const Kick& kick, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
-#define CALL(P, T) k_interpolate<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick);
+#define CALL(P, T) SCB_LAYOUT(k_interpolate<P, T, ST><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick, L);)
     SCB_DISPATCH_PT(CALL)
 #undef CALL
     return cudaGetLastError();
 }
 
 cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
-                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s) {
+                                 const void* q, void* tiles, void* rho, const Geom3& g, int accumulate, cudaStream_t s,
+                                 const PLayout* lay) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     cudaError_t e = cudaMemsetAsync(tiles, 0, (size_t)4 * ng * (mdt == 1 ? 8 : 4), s);
     if (e != cudaSuccess) return e;
     if (np > 0) {
         const unsigned grid = particle_grid(np, 256, 64);
-#define CALL(P, T) k_deposit_tiles<P, T><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)tiles, g);
+#define CALL(P, T) SCB_LAYOUT(k_deposit_tiles<P, T, ST><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)tiles, g, L);)
         SCB_DISPATCH_PT(CALL)
 #undef CALL
     }
@@ -706,23 +724,23 @@ cudaError_t launch_pack_efield(int mdt, const void* efield, void* packed, const 
 
 cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                       const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
-                                      const Kick& kick) {
+                                      const Kick& kick, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
     const unsigned grid = particle_grid(np, 256, 64);
     static const int imode = interp_mode();
-    const bool thread_per_particle = imode == 1;
+    const bool thread_per_particle = imode == 1 && !lay;   // the tuning variants exist for contiguous arrays only
     if (mdt == 1 && thread_per_particle) {
         if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
-    } else if (mdt == 1 && imode != 3) {
-        if (pdt == 1) k_interpolate_pair2_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
-        else k_interpolate_pair2_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
+    } else if (mdt == 1 && (imode != 3 || lay)) {
+        if (pdt == 1) { SCB_LAYOUT(k_interpolate_pair2_f64<double, ST><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);) }
+        else { SCB_LAYOUT(k_interpolate_pair2_f64<float, ST><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);) }
     } else if (mdt == 1) {
         if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else {
-        if (pdt == 1) k_interpolate_packed_f32<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
-        else k_interpolate_packed_f32<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
+        if (pdt == 1) { SCB_LAYOUT(k_interpolate_packed_f32<double, ST><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);) }
+        else { SCB_LAYOUT(k_interpolate_packed_f32<float, ST><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);) }
     }
     return cudaGetLastError();
 }
@@ -745,13 +763,13 @@ cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, con
 }
 
 cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z, double* out6,
-                          cudaStream_t s) {
+                          cudaStream_t s, const PLayout* lay) {
     unsigned long long* o = reinterpret_cast<unsigned long long*>(out6);
     k_bounds_init<<<1, 32, 0, s>>>(o);
     if (np > 0) {
         const unsigned grid = particle_grid(np, 256, 16);
-        if (pdt == 0) k_bounds<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, o);
-        else k_bounds<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, o);
+        if (pdt == 0) { SCB_LAYOUT(k_bounds<float, ST><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, o, L);) }
+        else { SCB_LAYOUT(k_bounds<double, ST><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, o, L);) }
     }
     return cudaGetLastError();
 }

@@ -300,4 +300,73 @@ end
 
 step_host_wait!(mesh::Mesh3D) = (h = handle(mesh); check(h, ccall((:scb_step_host_wait, LIB), Cint, (Ptr{Cvoid},), h.ptr)))
 
+# ---- strided / array-of-structures particle records (extension, scb_*_strided) -------------------
+# Mirrors `scb_particle_strides` (include/spacecharge_b200.h): ELEMENT strides of the seven particle arrays.
+struct ParticleStrides
+    x::Int64; y::Int64; z::Int64; q::Int64
+    ex::Int64; ey::Int64; ez::Int64
+    reserved::Int64
+end
+
+"""
+    deposit!(mesh, records::CuMatrix, q; rows=(1, 3, 5), clear=true)
+
+`deposit!` on Bmad-style phase-space records: `records` is a `(6, Np)` matrix `(x, px, y, py, z, pz)` per column;
+the coordinates are read in place (scb_deposit_strided, element stride `size(records, 1)`).  `q` is a dense charge
+vector, or a single number for equal-weight macro-particles (charge stride 0).
+"""
+function deposit!(mesh::Mesh3D{T}, records::CuMatrix{P}, q; rows::NTuple{3, Int} = (1, 3, 5), clear::Bool = true) where {T, P}
+    np = size(records, 2)
+    qarr = q isa Number ? CuArray(P[q]) : q
+    st = Ref(ParticleStrides(size(records, 1), size(records, 1), size(records, 1), q isa Number ? 0 : 1, 1, 1, 1, 0))
+    xs, ys, zs = (pointer(records, r) for r in rows)
+    h = handle(mesh)
+    GC.@preserve records qarr check(h, ccall((:scb_deposit_strided, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{ParticleStrides}, Cint,
+                    CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                   h.ptr, np, xs, ys, zs, qarr, st, dtag(P), mesh.rho, dtag(T), _n(mesh), _f3(mesh.min_bounds),
+                   _f3(mesh.delta), clear ? 1 : 0))
+end
+
+"""
+    interpolate_kick!(mesh, records::CuMatrix, coef_xy, coef_z; rows=(1, 3, 5), prows=(2, 4, 6))
+
+Gather fused with the momentum update on the same records (scb_interpolate_kick_strided): rows `rows` are read, rows
+`prows` are updated in place, the bunch is never copied or de-interleaved.
+"""
+function interpolate_kick!(mesh::Mesh3D{T}, records::CuMatrix{P}, coef_xy::Real, coef_z::Real;
+                           rows::NTuple{3, Int} = (1, 3, 5), prows::NTuple{3, Int} = (2, 4, 6)) where {T, P}
+    s = size(records, 1)
+    st = Ref(ParticleStrides(s, s, s, 1, s, s, s, 0))
+    xs, ys, zs = (pointer(records, r) for r in rows)
+    pxs, pys, pzs = (pointer(records, r) for r in prows)
+    h = handle(mesh)
+    GC.@preserve records check(h, ccall((:scb_interpolate_kick_strided, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{ParticleStrides}, Cint, CuPtr{Cvoid}, Cint,
+                    Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64),
+                   h.ptr, size(records, 2), xs, ys, zs, st, dtag(P), mesh.efield, dtag(T), _n(mesh), _f3(mesh.min_bounds),
+                   _f3(mesh.delta), pxs, pys, pzs, Float64(coef_xy), Float64(coef_z)))
+end
+
+"""
+    interpolate_field(mesh, records::CuMatrix; rows=(1, 3, 5)) -> (Ex, Ey, Ez)
+
+`interpolate_field` with the coordinates read from the records in place (scb_interpolate_strided); the outputs are
+fresh dense vectors like the reference's.
+"""
+function interpolate_field(mesh::Mesh3D{T}, records::CuMatrix{P}; rows::NTuple{3, Int} = (1, 3, 5)) where {T, P}
+    np = size(records, 2)
+    s = size(records, 1)
+    Ex = CuArray{P}(undef, np); Ey = similar(Ex); Ez = similar(Ex)
+    st = Ref(ParticleStrides(s, s, s, 1, 1, 1, 1, 0))
+    xs, ys, zs = (pointer(records, r) for r in rows)
+    h = handle(mesh)
+    GC.@preserve records check(h, ccall((:scb_interpolate_strided, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{ParticleStrides}, Cint, CuPtr{Cvoid}, Cint,
+                    Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}),
+                   h.ptr, np, xs, ys, zs, st, dtag(P), mesh.efield, dtag(T), _n(mesh), _f3(mesh.min_bounds),
+                   _f3(mesh.delta), Ex, Ey, Ez))
+    return Ex, Ey, Ez
+end
+
 end # module SpaceChargeB200
