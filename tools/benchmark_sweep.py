@@ -4,7 +4,10 @@ sigma = 1e-3 m, Q = 1e-9 C, seed 42; mesh construction and host->device copies o
 statistic = minimum over repetitions (@belapsed).  GPU = this library through the C ABI; CPU = the
 C restatement of the reference's structure (oracle/cpu_reference.py), timed on the host cores.
 
-usage: python tools/benchmark_sweep.py [--no-cpu] [--reps 10]"""
+--deposit adds the deposit-only table of benchmark/deposit_benchmark.jl:16-20 (anisotropic bunch sigma = (0.5, 0.3, 0.2),
+q = 1e-12 per particle, charge-conservation error in percent as the reference prints it).
+
+usage: python tools/benchmark_sweep.py [--no-cpu] [--reps 10] [--deposit]"""
 import argparse
 import json
 import os
@@ -42,12 +45,35 @@ def gpu_times(scb, grid, x, y, z, q, reps):
     return best, mesh
 
 
+def deposit_table(scb, reps):
+    """benchmark/deposit_benchmark.jl: compare_cpu_gpu_deposit over the six configurations (GPU side)."""
+    rows = []
+    print("%-8s %-9s | %9s %14s" % ("grid", "particles", "dep ms", "charge err %"))
+    for grid, n in CONFIGS:
+        rng = np.random.default_rng(42)
+        x, y, z = (rng.standard_normal(n) * s for s in (0.5, 0.3, 0.2))
+        q = np.ones(n) * 1e-12
+        d = [torch.from_numpy(a).cuda() for a in (x, y, z, q)]
+        mesh = scb.Mesh3D(grid, *d[:3])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(reps + 2):
+            e0.record(); scb.deposit_(mesh, *d); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        err = abs(q.sum() - float(mesh.rho.sum())) / q.sum() * 100
+        rows.append({"grid": grid[0], "particles": n, "deposit_ms": best, "charge_error_percent": err})
+        print("%-8s %-9d | %9.4f %14.2e" % ("%d^3" % grid[0], n, best, err))
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--deposit", action="store_true")
     args = ap.parse_args()
     scb = load_package()
+    dep_rows = deposit_table(scb, args.reps) if args.deposit else None
     rows = []
     print("%-8s %-9s | %9s %9s %9s %9s | %10s %8s" % ("grid", "particles", "dep ms", "solve ms", "interp ms", "pipe ms", "CPU pipe ms", "speedup"))
     for grid, n in CONFIGS:
@@ -71,7 +97,7 @@ def main():
             "%.1f" % cpu if cpu else "-", "%.0fx" % (cpu / g["pipeline"]) if cpu else "-"))
     out = os.path.join(ROOT, "gpurun_out", "benchmark_sweep.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    json.dump({"cores": os.cpu_count(), "rows": rows}, open(out, "w"), indent=1)
+    json.dump({"cores": os.cpu_count(), "rows": rows, "deposit_only": dep_rows}, open(out, "w"), indent=1)
 
 
 if __name__ == "__main__":
