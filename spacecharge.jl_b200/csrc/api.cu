@@ -103,6 +103,11 @@ struct scb_handle {
     // slab-decomposed step: field slabs broadcast on comm_stream, repacked on pack_stream, gathered on the main stream
     cudaStream_t comm_stream = nullptr, pack_stream = nullptr;
     cudaEvent_t ev_field = nullptr, ev_bcast[SCB_MAX_RANKS] = {}, ev_pack[SCB_MAX_RANKS] = {};
+    // cold geometry inside a fused step: the Green spectrum is rebuilt on green_stream (high priority) while the
+    // deposit runs on the main stream; the solve waits for ev_green_done
+    cudaStream_t green_stream = nullptr;
+    cudaEvent_t ev_green_start = nullptr, ev_green_done = nullptr;
+    bool green_pending = false;
 };
 
 namespace {
@@ -689,6 +694,10 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
             if (e.key == make_key(pl, delta, gamma, zero3, mdt, 0)) gfree = &e;
     }
     if (mode == 2) SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 2), &gaux, nc));
+    if (h->green_pending) {   // spectrum built on green_stream by prefetch_green: join before the passes
+        SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_green_done, 0));
+        h->green_pending = false;
+    }
 
     const size_t szA = (size_t)pl.PX * pl.n[1] * pl.n[2];
     const size_t szB = (size_t)pl.PX * pl.L[1] * pl.n[2];
@@ -887,6 +896,61 @@ double image_offset_z(int mdt, double min_z, double max_z) {
     return 2.0 * min_z + (max_z - min_z);
 }
 
+bool green_overlap_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SCB_GREEN_OVERLAP"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
+bool green_cached(const scb_handle* h, const GreenKey& key) {
+    for (const auto& e : h->green)
+        if (e.key == key && e.ncomp >= 3) return true;
+    return false;
+}
+
+// Fused steps on a NEW geometry (a tracking loop re-fits the mesh to the bunch every step, so the cached spectrum
+// misses every time): build the Green spectrum on a second, high-priority stream while the deposit runs on the main
+// stream.  The two stress different units -- the point-wise IGF is FP64-bound and the spectrum passes stream through
+// HBM, the deposit is bound by the L2 reduction path and uses a third of the DRAM bandwidth -- so most of the build
+// hides behind the deposit.  The build only touches the arena and the spectrum buffers, the deposit only rho and the
+// tile accumulator.  No-op when the spectrum is cached (the warm path) or the cache is disabled.
+int prefetch_green(scb_handle* h, int mdt, const int64_t n[3], const double min_bounds[3], const double max_bounds[3],
+                   const double delta[3], double gamma, int at_cathode) {
+    if (!green_overlap_enabled() || !h->opt.green_cache || h->green_pending) return SCB_OK;
+    if (!valid_dt(mdt) || !n || !min_bounds || !max_bounds || !delta || !(gamma > 0.0)) return SCB_OK;   // the solve reports it
+    for (int a = 0; a < 3; ++a)
+        if (n[a] < 2 || n[a] > kMaxFftLen / 2 || !(delta[a] > 0.0)) return SCB_OK;
+    const Plan pl = make_plan(n);
+    const double zero3[3] = {0, 0, 0};
+    double offset[3] = {0.0, 0.0, 0.0};
+    if (at_cathode) offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
+    const GreenKey kfree = make_key(pl, delta, gamma, zero3, mdt, 0);
+    const GreenKey kimg = make_key(pl, delta, gamma, offset, mdt, 1);
+    if (green_cached(h, kfree) && (!at_cathode || green_cached(h, kimg))) return SCB_OK;
+    if (!h->green_stream) {
+        int lo = 0, hi = 0;
+        SCB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SCB_CUDA(h, cudaStreamCreateWithPriority(&h->green_stream, cudaStreamNonBlocking, hi));
+        SCB_CUDA(h, cudaEventCreateWithFlags(&h->ev_green_start, cudaEventDisableTiming));
+        SCB_CUDA(h, cudaEventCreateWithFlags(&h->ev_green_done, cudaEventDisableTiming));
+    }
+    // everything queued so far (the previous solve's passes use the arena) comes first
+    SCB_CUDA(h, cudaEventRecord(h->ev_green_start, h->stream));
+    SCB_CUDA(h, cudaStreamWaitEvent(h->green_stream, h->ev_green_start, 0));
+    cudaStream_t main_stream = h->stream;
+    const bool timing = h->timing;
+    h->stream = h->green_stream;   // the build launches on h->stream
+    h->timing = false;             // its events would land on the side stream
+    const GreenEntry* unused = nullptr;
+    int rc = get_green(h, pl, kfree, &unused);
+    if (rc == SCB_OK && at_cathode) rc = get_green(h, pl, kimg, &unused);
+    h->stream = main_stream;
+    h->timing = timing;
+    if (rc != SCB_OK) return rc;
+    SCB_CUDA(h, cudaEventRecord(h->ev_green_done, h->green_stream));
+    h->green_pending = true;
+    return SCB_OK;
+}
+
 double key_to_double(unsigned long long k) {
     unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
     double d;
@@ -934,7 +998,8 @@ int scb_destroy(scb_handle* h) {
     for (cudaEvent_t e : h->ev_bcast) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pack) if (e) cudaEventDestroy(e);
     if (h->ev_field) cudaEventDestroy(h->ev_field);
-    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream, h->comm_stream, h->pack_stream})
+    for (cudaEvent_t e : {h->ev_green_start, h->ev_green_done}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream, h->comm_stream, h->pack_stream, h->green_stream})
         if (cs) {
             cudaStreamSynchronize(cs);
             cudaStreamDestroy(cs);
@@ -1176,6 +1241,7 @@ int scb_step(scb_handle* h, int64_t np, const void* x, const void* y, const void
              void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
              const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* ex, void* ey,
              void* ez) {
+    if (h && np > 0) SCB_TRY(prefetch_green(h, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     SCB_TRY(scb_deposit(h, np, x, y, z, q, pdt, rho, mdt, n, min_bounds, delta, 1));
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     return scb_interpolate(h, np, x, y, z, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
@@ -1279,6 +1345,7 @@ int scb_step_strided(scb_handle* h, int64_t np, const void* x, const void* y, co
                      const scb_particle_strides* st, int pdt, void* rho, void* efield, int mdt, const int64_t n[3],
                      const double min_bounds[3], const double max_bounds[3], const double delta[3], double gamma,
                      int at_cathode, void* ex, void* ey, void* ez) {
+    if (h && np > 0) SCB_TRY(prefetch_green(h, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     SCB_TRY(scb_deposit_strided(h, np, x, y, z, q, st, pdt, rho, mdt, n, min_bounds, delta, 1));
     SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     return scb_interpolate_strided(h, np, x, y, z, st, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
@@ -1328,6 +1395,7 @@ int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* y
         cev.push_back(e);
     }
     const Geom3 g = make_geom(n, min_bounds, delta);
+    SCB_TRY(prefetch_green(h, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));   // hides behind the upload
     if (h->host_steps_in_flight == 0) {
         // first step of a pipeline: the upload waits for whatever the caller queued before this call
         SCB_CUDA(h, cudaEventRecord(cev[2 * nchunk], h->stream));

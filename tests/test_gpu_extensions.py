@@ -116,3 +116,31 @@ def test_interpolate_kick_matches_oracle(scb, oracle, record, pdt, mdt, tol, n):
     for g, p, ec in zip(mom2, p0, (ex, ey, ez)):
         assert np.array_equal(g.cpu().numpy(), (p.astype(np.float64) + ec.cpu().numpy().astype(np.float64)).astype(pdt)) or \
             np.abs(g.cpu().numpy() - (p + ec.cpu().numpy())).max() <= 4 * np.finfo(pdt).eps * np.abs(p + ec.cpu().numpy()).max()
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_remesh_step_with_spectrum_prefetch_equals_separate_calls(scb, T, at_cathode):
+    """Tracking loop: remesh_ + the fused step on a new geometry builds the Green spectrum on a
+    second stream while the deposit runs (prefetch_green); the field must equal, bit for bit, what deposit_ / solve_ /
+    interpolate_field give on a mesh constructed from scratch for the same particles and the same rho."""
+    import torch
+    n, grid = 150_000, (20, 16, 24)
+    x, y, z, q = gaussian(n, 31, shift=(0, 0, 7e-3 if at_cathode else 0))
+    dx, dy, dz, dq = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D(grid, dx, dy, dz, T=T, gamma=2.5)
+    outs = [torch.empty_like(dx) for _ in range(3)]
+    scb.step_(mesh, dx, dy, dz, dq, *outs, at_cathode=at_cathode)          # warm: geometry 0 cached
+    for scale in (1.01, 0.97, 1.01):                                       # new, new, and back to a retired geometry
+        xs = dx * scale
+        mesh.remesh_(xs, dy, dz)
+        scb.step_(mesh, xs, dy, dz, dq, *outs, at_cathode=at_cathode)
+        fresh = scb.Mesh3D(grid, xs, dy, dz, T=T, gamma=2.5)
+        assert (fresh.min_bounds, fresh.max_bounds, fresh.delta) == (mesh.min_bounds, mesh.max_bounds, mesh.delta)
+        fresh.rho.copy_(mesh.rho)                                          # (reductions: rho itself is not bit-reproducible)
+        fresh.handle.drop_green_cache()                                    # rebuilt inside solve_, on the main stream
+        scb.solve_(fresh, at_cathode=at_cathode)
+        want = scb.interpolate_field(fresh, xs, dy, dz)
+        assert torch.equal(mesh.efield, fresh.efield)
+        for a, b in zip(outs, want):
+            assert torch.equal(a, b)
