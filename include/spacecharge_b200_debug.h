@@ -34,6 +34,13 @@ SCB_API int scb_debug_fft_x_r2c(scb_handle* h, int dt, int N, const void* in_rea
 SCB_API int scb_debug_fft_x_c2r(scb_handle* h, int dt, int N, const void* in_cplx, void* out_real,
                                 int64_t nlines, int64_t real_sline, int n_real, int PX, double scale);
 
+/* Measurement only (bench.py): ceiling of the scattered 32-byte sector traffic that bounds the particle passes.
+ * mode 0: lane pairs issue the gather's 256-bit no-allocate loads at two adjacent pseudo-random records of a zeroed buffer of
+ * buffer_bytes; mode 1: every four-lane group issues the tile deposit's fp64 reduction into a random 32-byte tile.
+ * Nothing else runs in the kernel.  Synchronous; returns 32-byte sector operations per second (best of three warm
+ * repetitions, CUDA events).  A buffer smaller than the L2 measures the L2 itself, a larger one adds DRAM misses. */
+SCB_API int scb_debug_l2_probe(scb_handle* h, int mode, int64_t buffer_bytes, int iters, double* sector_ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif

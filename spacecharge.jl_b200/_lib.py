@@ -101,6 +101,7 @@ SIGNATURES = {
     "scb_debug_fft_lines": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double]),
     "scb_debug_fft_x_r2c": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "scb_debug_l2_probe": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double)]),
     "scb_debug_fft_x_c2r": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double]),
 }
 

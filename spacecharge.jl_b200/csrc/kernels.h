@@ -80,4 +80,8 @@ cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, con
 cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z,
                           double* out6, cudaStream_t s, const PLayout* lay = nullptr);
 
+// measurement only: mode 0 = random 256-bit sector reads, mode 1 = random four-lane fp64 sector reductions over
+// `bytes` of `buf`; *ops receives the number of 32-byte sector operations the launch performs
+cudaError_t launch_probe(int mode, void* buf, size_t bytes, int iters, unsigned grid, cudaStream_t s, double* ops);
+
 }  // namespace scb

@@ -640,6 +640,63 @@ __global__ void __launch_bounds__(256) k_bounds(long long np, const P* __restric
     }
 }
 
+// ---- L2 probes (measurement only, scb_debug_l2_probe) -------------------------------------------
+// Ceilings for the scattered 32-byte sector traffic that bounds the particle passes: the gather issues 256-bit
+// no-allocate loads of random node records, the deposit four-lane fp64 reductions into random tile sectors.  The probes
+// issue exactly those instructions at pseudo-random sector addresses of a buffer (L2-resident when it is small) with
+// no other work, eight independent operations per thread and iteration; bench.py reports the particle kernels'
+// achieved sector rates against these measured ceilings next to the HBM-byte roofline.
+__device__ __forceinline__ unsigned long long lcg(unsigned long long s) {
+    return s * 6364136223846793005ull + 1442695040888963407ull;
+}
+
+__global__ void __launch_bounds__(256) k_probe_sector_reads(const double4* __restrict__ buf, unsigned long long nrec,
+                                                             int iters, double* __restrict__ sink) {
+    // two adjacent lanes fetch two adjacent records (the x-neighbours of the lane-pair gather): 32 sectors and about 20
+    // distinct 128-byte lines per warp instruction, like k_interpolate_pair2_f64
+    unsigned long long s = ((((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1) + 1) * 0x9E3779B97F4A7C15ull;
+    const unsigned long long pol = l2_policy(1);
+    const int kx = threadIdx.x & 1;
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        double v[8][4];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s = lcg(s);
+            ld256(buf + __umulhi((unsigned)(s >> 32), (unsigned)(nrec - 1)) + kx, v[k], pol);   // uniform in [0, nrec-1)
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += v[k][0];
+    }
+    if (acc == 0.123456789) sink[0] = acc;   // never true for a zeroed buffer; keeps the loads observable
+}
+
+__global__ void __launch_bounds__(256) k_probe_sector_reds(double* __restrict__ buf, unsigned long long ntile, int iters) {
+    // four adjacent lanes share one random tile (one 32-byte sector), like k_deposit_tiles
+    unsigned long long s = ((((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2) + 1) * 0x9E3779B97F4A7C15ull;
+    const unsigned long long pol = l2_policy(1);
+    const int k = threadIdx.x & 3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = lcg(s);
+            red_add_hint(buf + 4ull * __umulhi((unsigned)(s >> 32), (unsigned)ntile) + k, 1.0, pol);
+        }
+    }
+}
+
+cudaError_t launch_probe(int mode, void* buf, size_t bytes, int iters, unsigned grid, cudaStream_t s, double* ops) {
+    const unsigned long long nrec = bytes / 32;
+    if (mode == 0) {
+        k_probe_sector_reads<<<grid, 256, 0, s>>>((const double4*)buf, nrec, iters, (double*)buf);
+        *ops = (double)grid * 256.0 * iters * 8.0;          // one sector (one record) per lane and load
+    } else {
+        k_probe_sector_reds<<<grid, 256, 0, s>>>((double*)buf, nrec, iters);
+        *ops = (double)grid * 64.0 * iters * 8.0;           // one sector per four-lane group and reduction
+    }
+    return cudaGetLastError();
+}
+
 // ---- launchers -----------------------------------------------------------------------------
 static inline unsigned particle_grid(long long np, int bs, int per_sm) {
     long long want = (np + bs - 1) / bs;
