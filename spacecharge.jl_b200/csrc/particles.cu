@@ -12,6 +12,14 @@
 
 #include <cstdlib>
 
+// minimum resident CTAs per SM requested for the Float64 lane-pair gather (register cap = 65536 / (256 * SCB_GATHER_MINB)).
+// Measured at 1e8 particles / 256^3 (profiles/r01_ab_gather_occupancy_s5.log): 4 CTAs 3.20 ms, 5 CTAs (48 registers, the
+// compiler's own choice) 2.88 ms, 6 CTAs (40 registers, no spill) 2.85 ms, 8 CTAs (32 registers, 16 bytes spilled) 3.51 ms.
+// build.py -D SCB_GATHER_MINB=<n> builds a variant for A/B timing
+#ifndef SCB_GATHER_MINB
+#define SCB_GATHER_MINB 6
+#endif
+
 namespace scb {
 
 template <typename P, typename T> struct promote { using type = double; };
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
 // stores the result (16 active lanes, one 128-byte line): 12 shuffle wavefronts per 32 particles remain (the x0 + x1
 // halves of the three components).  Same arithmetic, bit-identical results.
 template <typename P, bool ST>
-__global__ void __launch_bounds__(256) k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
+__global__ void __launch_bounds__(256, SCB_GATHER_MINB) k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
                                                                 const P* __restrict__ y, const P* __restrict__ z,
                                                                 const double4* __restrict__ e, const Geom3 g,
                                                                 P* __restrict__ ex, P* __restrict__ ey,
@@ -705,6 +713,16 @@ static inline unsigned particle_grid(long long np, int bs, int per_sm) {
     return (unsigned)(want < cap ? want : cap);
 }
 
+// CTAs per SM of the grid-stride tile deposit and packed gather (tuning: SCB_DEPOSIT_PER_SM / SCB_GATHER_PER_SM).
+// Measured at 1e8 particles / 256^3 Float64 (profiles/r01_ab_particle_grid_s5.log): a grid of exactly the resident
+// CTAs runs all warps in lockstep through the load / gather / store phases (gather 4.2 ms at 5 per SM, deposit 1.97 ms at
+// 4 per SM); from 64 per SM on the curve is flat (gather 2.85 / 2.83 / 2.825 / 2.84 ms at 64 / 128 / 256 / 512).
+static int per_sm_env(const char* name) {
+    const char* e = getenv(name);
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 256;
+}
+
 #define SCB_DISPATCH_PT(CALL)                                                  \
     if (pdt == 0 && mdt == 0) { CALL(float, float) }                           \
     else if (pdt == 0 && mdt == 1) { CALL(float, double) }                     \
@@ -750,7 +768,8 @@ cudaError_t launch_deposit_tiles(int pdt, int mdt, long long np, const void* x, 
     cudaError_t e = cudaMemsetAsync(tiles, 0, (size_t)4 * ng * (mdt == 1 ? 8 : 4), s);
     if (e != cudaSuccess) return e;
     if (np > 0) {
-        const unsigned grid = particle_grid(np, 256, 64);
+        static const int per_sm = per_sm_env("SCB_DEPOSIT_PER_SM");
+        const unsigned grid = particle_grid(np, 256, per_sm);
 #define CALL(P, T) SCB_LAYOUT(k_deposit_tiles<P, T, ST><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)tiles, g, L);)
         SCB_DISPATCH_PT(CALL)
 #undef CALL
@@ -783,7 +802,8 @@ cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void
                                       const void* packed, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
                                       const Kick& kick, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
-    const unsigned grid = particle_grid(np, 256, 64);
+    static const int per_sm = per_sm_env("SCB_GATHER_PER_SM");
+    const unsigned grid = particle_grid(np, 256, per_sm);
     static const int imode = interp_mode();
     const bool thread_per_particle = imode == 1 && !lay;   // the tuning variants exist for contiguous arrays only
     if (mdt == 1 && thread_per_particle) {
