@@ -161,7 +161,7 @@ def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=1
     }
 
 
-def main():
+def main(print=print):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -425,28 +425,43 @@ def main():
                "blocking_call": {"api": "scb_step_host", "ms_per_step": 1e3 * t_sync, "value": npart / t_sync, "steps": bsteps}}
         del houts
     elif not args.no_e2e:
-        # sharded: every rank feeds its own shard from pinned host memory
+        # particle shards: every rank feeds its own shard from pinned host memory through scb_step_host_sharded_async
+        # (same two-slot pipeline as on one GPU; the collectives of the solve run on the handle's stream)
         hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
-        hex_, hey, hez = (torch.empty_like(hx).pin_memory() for _ in range(3))
+        houts = [[torch.empty_like(hx).pin_memory() for _ in range(3)] for _ in range(2)]
+        for _ in range(2):
+            scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)
+        ksteps = max(2, args.steps)
+        bsteps = max(2, min(args.steps, 4))
 
-        def host_step():
-            x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
-            z.copy_(hz, non_blocking=True); q.copy_(hq, non_blocking=True)
-            scb.step_(mesh, x, y, z, q, ex, ey, ez, at_cathode=at_cathode)
-            hex_.copy_(ex, non_blocking=True); hey.copy_(ey, non_blocking=True); hez.copy_(ez, non_blocking=True)
-            torch.cuda.synchronize()
-        host_step()
-        ksteps = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            host_step()
-        barrier()
-        tt = torch.tensor([(time.perf_counter() - t0) / ksteps], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": npart / float(tt.item()), "unit": "particles/s", "h2d_bytes_per_step": 4 * n_local * s,
-               "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * float(tt.item()), "steps": ksteps,
-               "api": "pinned host shards -> step_ -> pinned host outputs, per rank"}
+        def timed(fn, k):
+            barrier()
+            t0 = time.perf_counter()
+            fn(k)
+            barrier()
+            tt = torch.tensor([(time.perf_counter() - t0) / k], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        def blocking(k):
+            for _ in range(k):
+                scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)
+
+        def pipelined(k):
+            for i in range(k):
+                scb.step_host_async_(mesh, hx, hy, hz, hq, *houts[i & 1], at_cathode=at_cathode)
+            scb.step_host_wait_(mesh)
+
+        t_sync = timed(blocking, bsteps)
+        pipelined(2)
+        t_e2e = timed(pipelined, ksteps)
+        e2e = {"value": npart / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": 4 * n_local * s,
+               "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * t_e2e, "steps": ksteps,
+               "api": "per rank: scb_step_host_sharded_async x steps + scb_step_host_wait (pinned host shard in, pinned host E "
+                      "out; consecutive steps overlap upload and download); bytes are per rank",
+               "blocking_call": {"api": "scb_step_host_sharded_async + scb_step_host_wait per step", "ms_per_step": 1e3 * t_sync,
+                                 "value": npart / t_sync, "steps": bsteps}}
+        del houts
 
     # secondary baseline: the reference's GPU structure (1 thread/particle atomics, 7 in-place Z2Z cuFFTs and
     # ~20 element-wise launches per solve, 24-gather interpolation) restated in plain CUDA, on the same GPU
@@ -497,5 +512,30 @@ def main():
         dist.destroy_process_group()
 
 
+def _emit_only_json(fn):
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout when
+    NCCL_DEBUG is set on the box), so file descriptor 1 points at stderr while the benchmark runs and the line is
+    written to the real stdout at the end."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    builtin_print = print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(v) for v in a))
+        else:
+            builtin_print(*a, **k)
+    try:
+        fn(capture)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+        for ln in lines:
+            builtin_print(ln, flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    _emit_only_json(main)

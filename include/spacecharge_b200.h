@@ -253,6 +253,17 @@ SCB_API int scb_step_sharded(scb_handle* h, int64_t np, const void* x, const voi
                      const int64_t n[3], const double min_bounds[3], const double max_bounds[3],
                      const double delta[3], double gamma, int at_cathode, void* ex, void* ey, void* ez);
 
+/* scb_step_host_async for a particle shard: every rank passes its own HOST shard and output buffers, the grids are the
+ * rank's partial rho / the full efield as in scb_step_sharded.  slab_solve != 0: slab-decomposed solve (same divisibility
+ * rule as scb_solve_sharded); 0: rho all-reduced, solve replicated.  All ranks must queue the same sequence of steps;
+ * completion with scb_step_host_wait.  (The reference has no host-buffer or multi-device entry point; this is the
+ * sharded form of the benchmark body benchmark/full_pipeline_benchmark.jl:26-30.) */
+SCB_API int scb_step_host_sharded_async(scb_handle* h, int64_t np, const void* x_host, const void* y_host,
+                  const void* z_host, const void* q_host, int pdt, void* rho_partial, void* efield,
+                  int mdt, const int64_t n[3], const double min_bounds[3],
+                  const double max_bounds[3], const double delta[3], double gamma,
+                  int at_cathode, int slab_solve, void* ex_host, void* ey_host, void* ez_host);
+
 /* ---- cache control ------------------------------------------------------------------------ */
 SCB_API int scb_drop_green_cache(scb_handle* h);
 /* bytes of device workspace currently owned by the handle */

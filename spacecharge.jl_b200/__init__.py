@@ -590,6 +590,16 @@ def _step_host(fn_name, mesh, x, y, z, q, ex, ey, ez, at_cathode):
     hd.use_current_stream()
     (px, dt), (py, _), (pz, _), (pq, _) = (_host_ptr(a) for a in (x, y, z, q))
     (pex, _), (pey, _), (pez, _) = (_host_ptr(a) for a in (ex, ey, ez))
+    if mesh.group is not None:
+        # particle shards: every rank feeds its own host shard (scb_step_host_sharded_async)
+        hd.init_comm(mesh.group)
+        hd.check(hd.lib.scb_step_host_sharded_async(hd.h, len(x), px, py, pz, pq, _tag(dt), mesh._rho.data_ptr(),
+                                                    mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(),
+                                                    mesh._d(), float(mesh.gamma), 1 if at_cathode else 0,
+                                                    1 if mesh.sharded else 0, pex, pey, pez))
+        if fn_name == "scb_step_host":
+            hd.check(hd.lib.scb_step_host_wait(hd.h))
+        return
     hd.check(getattr(hd.lib, fn_name)(hd.h, len(x), px, py, pz, pq, _tag(dt), mesh._rho.data_ptr(),
                                       mesh._efield.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(),
                                       float(mesh.gamma), 1 if at_cathode else 0, pex, pey, pez))
@@ -597,7 +607,8 @@ def _step_host(fn_name, mesh, x, y, z, q, ex, ey, ez, at_cathode):
 
 def step_host_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
     """The same step with HOST particle buffers (numpy arrays or CPU torch tensors, ideally
-    pinned): host->device and device->host copies are part of the call (scb_step_host)."""
+    pinned): host->device and device->host copies are part of the call (scb_step_host).  On a mesh built
+    with ``group=`` the buffers are this rank's particle shard (scb_step_host_sharded_async + wait)."""
     _step_host("scb_step_host", mesh, x, y, z, q, ex, ey, ez, at_cathode)
 
 

@@ -88,6 +88,8 @@ SIGNATURES = {
                                 _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
     "scb_step_host_async": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
                                       _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
+    "scb_step_host_sharded_async": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3,
+                                              _F64x3, _F64x3, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
     "scb_step_host_wait": (C.c_int, [_vp]),
     "scb_drop_green_cache": (C.c_int, [_vp]),
     "scb_workspace_bytes": (C.c_int64, [_vp]),

@@ -1351,11 +1351,13 @@ int scb_step_strided(scb_handle* h, int64_t np, const void* x, const void* y, co
     return scb_interpolate_strided(h, np, x, y, z, st, pdt, efield, mdt, n, min_bounds, delta, ex, ey, ez);
 }
 
-int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
-                        void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
-                        const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
-                        void* eyh, void* ezh) {
+// comm_mode 0: one GPU; 1: particle shards, rho all-reduced, solve replicated; 2: particle shards, slab-decomposed solve
+static int step_host_impl(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
+                          void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                          const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
+                          void* eyh, void* ezh, int comm_mode) {
     if (!h) return SCB_ERR_INVALID_ARG;
+    if (comm_mode != 0 && !h->comm) return fail(h, SCB_ERR_COMM, "scb_comm_init has not been called");
     if (np <= 0 || !xh || !yh || !zh || !qh || !exh || !eyh || !ezh || !rho || !efield || !valid_dt(pdt) || !valid_dt(mdt))
         return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_step_host");
     SCB_TRY(check_grid(h, n));
@@ -1395,7 +1397,8 @@ int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* y
         cev.push_back(e);
     }
     const Geom3 g = make_geom(n, min_bounds, delta);
-    SCB_TRY(prefetch_green(h, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));   // hides behind the upload
+    // hides behind the upload (the slab solve keeps its own slab of the spectrum and builds it inside the solve)
+    if (comm_mode != 2) SCB_TRY(prefetch_green(h, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
     if (h->host_steps_in_flight == 0) {
         // first step of a pipeline: the upload waits for whatever the caller queued before this call
         SCB_CUDA(h, cudaEventRecord(cev[2 * nchunk], h->stream));
@@ -1413,7 +1416,14 @@ int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* y
         SCB_CUDA(h, launch_deposit(pdt, mdt, m, d[0] + o * es, d[1] + o * es, d[2] + o * es, d[3] + o * es, rho, g, h->opt.deposit_mode, h->stream));
         h->launches += 1;
     }
-    SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    if (comm_mode == 2) {
+        SCB_TRY(scb_solve_sharded(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    } else {
+        if (comm_mode == 1)
+            SCB_NCCL(h, g_nccl.AllReduce(rho, rho, (size_t)n[0] * n[1] * n[2], mdt == SCB_F64 ? ncclFloat64 : ncclFloat32,
+                                         ncclSum, h->comm, h->stream));
+        SCB_TRY(scb_solve(h, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode));
+    }
     bool packed_ready = false;
     if (np * 4 >= (int64_t)n[0] * n[1] * n[2]) {
         SCB_TRY(ensure_packed(h, (size_t)n[0] * n[1] * n[2] * packed_bytes_per_node(mdt)));
@@ -1443,6 +1453,22 @@ int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* y
     h->slot_used[slot] = true;
     h->host_steps_in_flight += 1;
     return SCB_OK;
+}
+
+int scb_step_host_async(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh, int pdt,
+                        void* rho, void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
+                        const double max_bounds[3], const double delta[3], double gamma, int at_cathode, void* exh,
+                        void* eyh, void* ezh) {
+    return step_host_impl(h, np, xh, yh, zh, qh, pdt, rho, efield, mdt, n, min_bounds, max_bounds, delta, gamma, at_cathode,
+                          exh, eyh, ezh, 0);
+}
+
+int scb_step_host_sharded_async(scb_handle* h, int64_t np, const void* xh, const void* yh, const void* zh, const void* qh,
+                                int pdt, void* rho_partial, void* efield, int mdt, const int64_t n[3],
+                                const double min_bounds[3], const double max_bounds[3], const double delta[3], double gamma,
+                                int at_cathode, int slab_solve, void* exh, void* eyh, void* ezh) {
+    return step_host_impl(h, np, xh, yh, zh, qh, pdt, rho_partial, efield, mdt, n, min_bounds, max_bounds, delta, gamma,
+                          at_cathode, exh, eyh, ezh, slab_solve ? 2 : 1);
 }
 
 int scb_step_host_wait(scb_handle* h) {

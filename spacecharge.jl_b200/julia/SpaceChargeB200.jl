@@ -300,6 +300,77 @@ end
 
 step_host_wait!(mesh::Mesh3D) = (h = handle(mesh); check(h, ccall((:scb_step_host_wait, LIB), Cint, (Ptr{Cvoid},), h.ptr)))
 
+# ---- multi-GPU (extension; the reference is single-device): one Julia process and one handle per GPU ----------
+"""
+    comm_unique_id() -> Vector{UInt8}          (on one rank; broadcast the 128 bytes, e.g. with MPI.Bcast!)
+    comm_init!(mesh, nranks, rank, uid)        (on every rank)
+
+Create the library's NCCL communicator for the mesh's handle (scb_comm_unique_id / scb_comm_init).
+"""
+function comm_unique_id()
+    uid = zeros(UInt8, 128)
+    rc = ccall((:scb_comm_unique_id, LIB), Cint, (Ptr{UInt8},), uid)
+    rc == 0 || error("scb_comm_unique_id failed with code $rc (libnccl.so.2 not loadable?)")
+    return uid
+end
+comm_init!(mesh::Mesh3D, nranks::Integer, rank::Integer, uid::Vector{UInt8}) =
+    (h = handle(mesh); check(h, ccall((:scb_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h.ptr, nranks, rank, uid)))
+comm_destroy!(mesh::Mesh3D) = (h = handle(mesh); check(h, ccall((:scb_comm_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr)))
+
+"""
+    solve_sharded!(mesh; at_cathode=false)
+
+`solve!` for a particle-sharded run: `mesh.rho` holds this rank's partial charge grid (every rank deposited its own
+shard on the same geometry); slab-decomposed solve over NCCL / NVLink, every rank ends with the full `mesh.efield`
+(scb_solve_sharded).
+"""
+function solve_sharded!(mesh::Mesh3D{T}; at_cathode::Bool = false) where {T}
+    h = handle(mesh)
+    check(h, ccall((:scb_solve_sharded, LIB), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Float64, Cint),
+                   h.ptr, mesh.rho, mesh.efield, dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.max_bounds),
+                   _f3(mesh.delta), Float64(mesh.gamma), at_cathode ? 1 : 0))
+end
+
+"""
+    step_sharded!(mesh, x, y, z, q, Ex, Ey, Ez; at_cathode=false)
+
+`step!` on this rank's particle shard (scb_step_sharded).
+"""
+function step_sharded!(mesh::Mesh3D{T}, x, y, z, q, Ex, Ey, Ez; at_cathode::Bool = false) where {T}
+    P = eltype(x)
+    h = handle(mesh)
+    check(h, ccall((:scb_step_sharded, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid},
+                    CuPtr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                    CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}),
+                   h.ptr, length(x), x, y, z, q, dtag(P), mesh.rho, mesh.efield, dtag(T), _n(mesh),
+                   _f3(mesh.min_bounds), _f3(mesh.max_bounds), _f3(mesh.delta), Float64(mesh.gamma), at_cathode ? 1 : 0,
+                   Ex, Ey, Ez))
+end
+
+"""
+    step_host_sharded!(mesh, x, y, z, q, Ex, Ey, Ez; at_cathode=false, slab_solve=true)
+
+`step_host!(...; wait=false)` for one rank of a particle-sharded run (scb_step_host_sharded_async): the host arrays are
+this rank's shard, `mesh.rho` receives the rank's partial charge grid and `mesh.efield` the full field.  The handle must
+carry a communicator (`comm_init!`); every rank queues the same sequence of steps and finishes with `step_host_wait!`.
+"""
+function step_host_sharded!(mesh::Mesh3D{T}, x::Array{P}, y::Array{P}, z::Array{P}, q::Array{P}, Ex::Array{P},
+                            Ey::Array{P}, Ez::Array{P}; at_cathode::Bool = false, slab_solve::Bool = true) where {T,P}
+    h = handle(mesh)
+    GC.@preserve x y z q Ex Ey Ez begin
+        check(h, ccall((:scb_step_host_sharded_async, LIB), Cint,
+                       (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid},
+                        Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint, Cint, Ptr{Cvoid},
+                        Ptr{Cvoid}, Ptr{Cvoid}),
+                       h.ptr, length(x), pointer(x), pointer(y), pointer(z), pointer(q), dtag(P), mesh.rho, mesh.efield,
+                       dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.max_bounds), _f3(mesh.delta), Float64(mesh.gamma),
+                       at_cathode ? 1 : 0, slab_solve ? 1 : 0, pointer(Ex), pointer(Ey), pointer(Ez)))
+    end
+end
+
 # ---- strided / array-of-structures particle records (extension, scb_*_strided) -------------------
 # Mirrors `scb_particle_strides` (include/spacecharge_b200.h): ELEMENT strides of the seven particle arrays.
 struct ParticleStrides

@@ -68,6 +68,21 @@ def _worker(rank, world, port, out_dir):
                     err = float((mesh.efield[..., c] - ref.efield[..., c]).abs().max() / ref.efield[..., c].abs().max())
                     assert err < tol, (grid, cath, sharded, overlap, "step field", c, err)
             os.environ.pop("SCB_GATHER_OVERLAP", None)
+            # host-buffer shards (scb_step_host_sharded_async): one blocking step, then three queued back to back
+            hin = [t.cpu().pin_memory() for t in mine]
+            houts = [[torch.full_like(hin[0], float("nan")).pin_memory() for _ in range(3)] for _ in range(3)]
+            mesh.efield.zero_()
+            scb.step_host_(mesh, *hin, *houts[0], at_cathode=cath)
+            for k in range(3):
+                scb.step_host_async_(mesh, *hin, *houts[k], at_cathode=cath)
+            scb.step_host_wait_(mesh)
+            for k in range(3):
+                for c in range(3):
+                    err = float((houts[k][c].to(dev) - rex[c]).abs().max() / rex[c].abs().max())
+                    assert err < tol, (grid, cath, sharded, "host step interp", k, c, err)
+            for c in range(3):
+                err = float((mesh.efield[..., c] - ref.efield[..., c]).abs().max() / ref.efield[..., c].abs().max())
+                assert err < tol, (grid, cath, sharded, "host step field", c, err)
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("%g" % worst)
     dist.destroy_process_group()
 
