@@ -13,11 +13,18 @@
 #include <cstdlib>
 
 // minimum resident CTAs per SM requested for the Float64 lane-pair gather (register cap = 65536 / (256 * SCB_GATHER_MINB)).
-// Measured at 1e8 particles / 256^3 (profiles/r01_ab_gather_occupancy_s5.log): 4 CTAs 3.20 ms, 5 CTAs (48 registers, the
-// compiler's own choice) 2.88 ms, 6 CTAs (40 registers, no spill) 2.85 ms, 8 CTAs (32 registers, 16 bytes spilled) 3.51 ms.
+// Measured at 1e8 particles / 256^3 with the run-time slab filter still in the kernel
+// (profiles/r01_ab_gather_occupancy_s5.log): 4 CTAs 3.20 ms, 5 CTAs (48 registers, the compiler's own choice) 2.88 ms,
+// 6 CTAs (40 registers, no spill) 2.85 ms, 8 CTAs (32 registers, 16 bytes spilled) 3.51 ms; with the filter compiled out
+// (profiles/r01_ab_gather_filter_s5.log): 5 CTAs 2.61 ms, 6 CTAs 2.58 ms.
 // build.py -D SCB_GATHER_MINB=<n> builds a variant for A/B timing
 #ifndef SCB_GATHER_MINB
 #define SCB_GATHER_MINB 6
+#endif
+#if SCB_GATHER_MINB > 0
+#define SCB_GATHER_BOUNDS __launch_bounds__(256, SCB_GATHER_MINB)
+#else
+#define SCB_GATHER_BOUNDS __launch_bounds__(256)   // -D SCB_GATHER_MINB=0: the compiler's own register allocation
 #endif
 
 namespace scb {
@@ -439,8 +446,10 @@ __global__ void __launch_bounds__(256) k_interpolate_pair_f64(long long np, cons
 // themselves (same address: one wavefront per 16 particles and array), locate it redundantly, and the even lane
 // stores the result (16 active lanes, one 128-byte line): 12 shuffle wavefronts per 32 particles remain (the x0 + x1
 // halves of the three components).  Same arithmetic, bit-identical results.
-template <typename P, bool ST>
-__global__ void __launch_bounds__(256, SCB_GATHER_MINB) k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
+// FL = false (every caller except the slab passes of SCB_GATHER_OVERLAP) compiles the slab filter out: carrying it as a
+// run-time flag cost the plain gather 10 % (2.62 -> 2.88 ms at 1e8 particles; z loaded first, x and y conditional).
+template <typename P, bool ST, bool FL>
+__global__ void SCB_GATHER_BOUNDS k_interpolate_pair2_f64(long long np, const P* __restrict__ x,
                                                                 const P* __restrict__ y, const P* __restrict__ z,
                                                                 const double4* __restrict__ e, const Geom3 g,
                                                                 P* __restrict__ ex, P* __restrict__ ey,
@@ -457,8 +466,8 @@ __global__ void __launch_bounds__(256, SCB_GATHER_MINB) k_interpolate_pair2_f64(
     // latency-bound (ncu: long-scoreboard stalls 12 per issued instruction), and this takes the DRAM round trip of the
     // particle stream off the critical path of every iteration
     long long i = warp * 16 + (lane >> 1);
-    const bool filt = g.zlo > 0 || g.zhi < g.n[2];   // slab filter active (uniform)
-    const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
+    const bool filt = FL && (g.zlo > 0 || g.zhi < g.n[2]);   // slab filter active (uniform)
+    const bool zfirst = FL && g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
     if (i < np) {
         cz = ld_stream(z + pidx<ST>(i, L.z));
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(256, SCB_GATHER_MINB) k_interpolate_pair2_f64(
     }
 }
 
-template <typename P, bool ST>
+template <typename P, bool ST, bool FL>
 __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, const P* __restrict__ x,
                                                                  const P* __restrict__ y, const P* __restrict__ z,
                                                                  const float4* __restrict__ e, const Geom3 g,
@@ -518,8 +527,8 @@ __global__ void __launch_bounds__(256) k_interpolate_packed_f32(long long np, co
     const unsigned long long pol = l2_policy(g.l2_keep);
     // coordinates requested one iteration ahead (latency-bound gather, see k_interpolate_pair2_f64)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool filt = g.zlo > 0 || g.zhi < g.n[2];   // slab filter active (uniform)
-    const bool zfirst = g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
+    const bool filt = FL && (g.zlo > 0 || g.zhi < g.n[2]);   // slab filter active (uniform)
+    const bool zfirst = FL && g.zfirst != 0;   // x and y fetched on demand (slab passes that select few particles)
     P cx = 0, cy = 0, cz = 0;
     if (i < np) {
         cz = ld_stream(z + pidx<ST>(i, L.z));
@@ -734,6 +743,11 @@ static int per_sm_env(const char* name) {
     if (lay) { const PLayout L = *lay; constexpr bool ST = true; __VA_ARGS__ } \
     else { const PLayout L{}; constexpr bool ST = false; __VA_ARGS__ }
 
+// FL = true instantiations carry the z-slab filter of the overlapped field gather (needs `const Geom3& g` in scope)
+#define SCB_FILTER(...)                                                        \
+    if (g.zlo > 0 || g.zhi < g.n[2] || g.zfirst != 0) { constexpr bool FL = true; __VA_ARGS__ } \
+    else { constexpr bool FL = false; __VA_ARGS__ }
+
 cudaError_t launch_deposit(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                            const void* q, void* rho, const Geom3& g, int mode, cudaStream_t s, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
@@ -810,14 +824,14 @@ cudaError_t launch_interpolate_packed(int pdt, int mdt, long long np, const void
         if (pdt == 1) k_interpolate_packed_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_packed_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else if (mdt == 1 && (imode != 3 || lay)) {
-        if (pdt == 1) { SCB_LAYOUT(k_interpolate_pair2_f64<double, ST><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);) }
-        else { SCB_LAYOUT(k_interpolate_pair2_f64<float, ST><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);) }
+        if (pdt == 1) { SCB_LAYOUT(SCB_FILTER(k_interpolate_pair2_f64<double, ST, FL><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);)) }
+        else { SCB_LAYOUT(SCB_FILTER(k_interpolate_pair2_f64<float, ST, FL><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);)) }
     } else if (mdt == 1) {
         if (pdt == 1) k_interpolate_pair_f64<double><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const double4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick);
         else k_interpolate_pair_f64<float><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const double4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick);
     } else {
-        if (pdt == 1) { SCB_LAYOUT(k_interpolate_packed_f32<double, ST><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);) }
-        else { SCB_LAYOUT(k_interpolate_packed_f32<float, ST><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);) }
+        if (pdt == 1) { SCB_LAYOUT(SCB_FILTER(k_interpolate_packed_f32<double, ST, FL><<<grid, 256, 0, s>>>(np, (const double*)x, (const double*)y, (const double*)z, (const float4*)packed, g, (double*)ex, (double*)ey, (double*)ez, kick, L);)) }
+        else { SCB_LAYOUT(SCB_FILTER(k_interpolate_packed_f32<float, ST, FL><<<grid, 256, 0, s>>>(np, (const float*)x, (const float*)y, (const float*)z, (const float4*)packed, g, (float*)ex, (float*)ey, (float*)ez, kick, L);)) }
     }
     return cudaGetLastError();
 }
