@@ -47,3 +47,19 @@ def test_no_cpu_fallback(scb):
     src = open(os.path.join(ROOT, "spacecharge.jl_b200", "__init__.py")).read() + \
         open(os.path.join(ROOT, "spacecharge.jl_b200", "_lib.py")).read()
     assert "oracle" not in src.replace("the oracle", "")
+
+
+def test_ctypes_prototypes_match_the_header(scb):
+    """Argument count and kind (pointer / int64 / int / double) of every ctypes prototype against the C declaration."""
+    import ctypes as C
+    from test_julia_shim_signatures import header_prototypes
+    _lib = scb._lib
+
+    def kind(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C.Array):
+            return "ptr"
+        return {C.c_int64: "i64", C.c_int: "i32", C.c_double: "f64"}[t]
+
+    protos = header_prototypes()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert [kind(t) for t in argtypes] == protos[name], name
