@@ -395,9 +395,18 @@ def main(print=print):
 
     # end to end: host (pinned) particle buffers through scb_step_host, copies inside the timed region
     e2e = None
+    # pinned host buffers are allocated with the process bound to the GPU's local cores (first-touch NUMA placement next
+    # to its PCIe root port); the previous affinity is restored right after, so the CPU baseline keeps every core
+    numa_bound = None
+    if not args.no_e2e:
+        old_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        bound = scb.bind_host_to_device(local_rank)
+        numa_bound = len(bound) if bound else None
     if not args.no_e2e and world == 1:
         hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
         houts = [[torch.empty_like(hx).pin_memory() for _ in range(3)] for _ in range(2)]
+        if bound:
+            os.sched_setaffinity(0, old_affinity)
         for _ in range(2):
             scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)
         ksteps = max(2, args.steps)       # the pipelined run times exactly --steps steps, like the device-resident run
@@ -422,13 +431,16 @@ def main(print=print):
                "d2h_bytes_per_step": 3 * n_local * s, "ms_per_step": 1e3 * t_e2e, "steps": ksteps,
                "api": "scb_step_host_async x steps + scb_step_host_wait (pinned host particle arrays in, pinned host E "
                       "arrays out; consecutive steps overlap upload and download over the full-duplex link)",
-               "blocking_call": {"api": "scb_step_host", "ms_per_step": 1e3 * t_sync, "value": npart / t_sync, "steps": bsteps}}
+               "blocking_call": {"api": "scb_step_host", "ms_per_step": 1e3 * t_sync, "value": npart / t_sync, "steps": bsteps},
+               "host_cores_bound_for_allocation": numa_bound}
         del houts
     elif not args.no_e2e:
         # particle shards: every rank feeds its own shard from pinned host memory through scb_step_host_sharded_async
         # (same two-slot pipeline as on one GPU; the collectives of the solve run on the handle's stream)
         hx, hy, hz, hq = (t_.cpu().pin_memory() for t_ in (x, y, z, q))
         houts = [[torch.empty_like(hx).pin_memory() for _ in range(3)] for _ in range(2)]
+        if bound:
+            os.sched_setaffinity(0, old_affinity)
         for _ in range(2):
             scb.step_host_(mesh, hx, hy, hz, hq, *houts[0], at_cathode=at_cathode)
         ksteps = max(2, args.steps)
@@ -460,7 +472,8 @@ def main(print=print):
                "api": "per rank: scb_step_host_sharded_async x steps + scb_step_host_wait (pinned host shard in, pinned host E "
                       "out; consecutive steps overlap upload and download); bytes are per rank",
                "blocking_call": {"api": "scb_step_host_sharded_async + scb_step_host_wait per step", "ms_per_step": 1e3 * t_sync,
-                                 "value": npart / t_sync, "steps": bsteps}}
+                                 "value": npart / t_sync, "steps": bsteps},
+               "host_cores_bound_for_allocation": numa_bound}
         del houts
 
     # secondary baseline: the reference's GPU structure (1 thread/particle atomics, 7 in-place Z2Z cuFFTs and

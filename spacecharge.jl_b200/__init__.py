@@ -24,7 +24,7 @@ from ._lib import LibraryMissing, ScbError  # noqa: F401
 __all__ = ["Mesh3D", "deposit_", "clear_mesh_", "interpolate_field", "solve_", "solve_freespace_",
            "get_green_function_", "cell_indices", "step_", "step_host_", "step_host_async_", "step_host_wait_", "ErrorException", "CLIGHT", "FPEI",
            "solve_potential_", "magnetic_field", "interpolate_kick_",
-           "Handle", "default_handle"]
+           "Handle", "default_handle", "bind_host_to_device"]
 
 CLIGHT = 299792458.0          # src/utils.jl:7
 FPEI = CLIGHT ** 2 * 1.0e-7   # src/utils.jl:8
@@ -144,6 +144,36 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+
+def bind_host_to_device(device: Optional[int] = None) -> Optional[list]:
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (its socket / NUMA node), so that
+    pinned host buffers allocated afterwards are placed next to the GPU's PCIe root port (first-touch policy) and the
+    host-buffer steps (scb_step_host*) do not cross the inter-socket link.  Call it before allocating the buffers.
+    Returns the CPU list that was set, or None when NVML, the affinity query or sched_setaffinity is unavailable or
+    SCB_NUMA_BIND=0.  Host plumbing only: no effect on any device result."""
+    import os
+    if os.environ.get("SCB_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    torch = _torch()
+    try:
+        import pynvml
+        if device is None:
+            device = torch.cuda.current_device()
+        prop = torch.cuda.get_device_properties(device)
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        allowed = sorted(local & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 _handles = {}

@@ -45,3 +45,22 @@ def test_shard_ranges_cover_everything(scb):
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [e - b for b, e in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_bind_host_to_device_is_harmless_without_a_gpu(scb):
+    """bind_host_to_device is host plumbing: without NVML / a GPU it returns None and leaves the affinity alone; with
+    SCB_NUMA_BIND=0 it never touches it."""
+    import os
+    if not hasattr(os, "sched_getaffinity"):
+        return
+    before = os.sched_getaffinity(0)
+    os.environ["SCB_NUMA_BIND"] = "0"
+    try:
+        assert scb.bind_host_to_device(0) is None
+    finally:
+        os.environ.pop("SCB_NUMA_BIND")
+    out = scb.bind_host_to_device(0)
+    try:
+        assert out is None or set(out) <= before
+    finally:
+        os.sched_setaffinity(0, before)
