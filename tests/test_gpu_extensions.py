@@ -144,3 +144,59 @@ def test_remesh_step_with_spectrum_prefetch_equals_separate_calls(scb, T, at_cat
         assert torch.equal(mesh.efield, fresh.efield)
         for a, b in zip(outs, want):
             assert torch.equal(a, b)
+
+
+def test_warm_step_is_capturable_in_a_cuda_graph(scb, record):
+    """The small configurations are launch-bound (nine launches of 5-10 us at 32^3), so a tracking loop wants the
+    step inside a CUDA graph.  In the warm state (workspace, packed field, Green spectrum built) scb_step performs no
+    allocation, synchronisation or cross-stream wait, i.e. it is legal under stream capture: capture it once, replay it
+    on new particle values in the same buffers, compare with direct calls."""
+    import time
+    import torch
+    grid = (32, 32, 32)
+    x, y, z, q = to_dev(*gaussian(100000, 21))
+    lo = tuple(1.5 * float(a.min()) for a in (x, y, z))
+    hi = tuple(1.5 * float(a.max()) for a in (x, y, z))
+    mesh = scb.Mesh3D(grid, lo, hi, gamma=1.5)
+    outs = [torch.empty_like(x) for _ in range(3)]
+
+    def direct():
+        scb.step_(mesh, x, y, z, q, *outs)
+        torch.cuda.synchronize()
+        return [o.clone() for o in outs], mesh.efield.clone()
+
+    direct()
+    want, e_want = direct()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        scb.step_(mesh, x, y, z, q, *outs)          # binds the handle to the capture stream, warm there
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            scb.step_(mesh, x, y, z, q, *outs)
+    for o in outs:
+        o.fill_(float("nan"))
+    g.replay()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())   # noqa: E731
+    for a, b in zip(outs, want):
+        assert rel(a, b) < 1e-12      # atomics: rounding-level differences between runs
+    assert rel(mesh.efield, e_want) < 1e-12
+    # new particle values in the captured buffers (still inside the fixed mesh)
+    x.mul_(0.7); y.mul_(-0.9); z.mul_(0.8)
+    g.replay()
+    torch.cuda.synchronize()
+    got = [o.clone() for o in outs]
+    want2, _ = direct()
+    for a, b in zip(got, want2):
+        assert rel(a, b) < 1e-12
+
+    def per_step(fn, n=200):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / n
+    record("basic config, direct step (ms)", per_step(lambda: scb.step_(mesh, x, y, z, q, *outs)))
+    record("basic config, graph replay (ms)", per_step(g.replay))
