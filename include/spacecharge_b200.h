@@ -57,7 +57,9 @@ typedef struct scb_options {
     int32_t green_cache;       /* 1 (default): keep the IGF spectrum per geometry; 0: rebuild every
                                   solve like the reference does (src/solvers/free_space.jl:79-89) */
     int32_t deposit_mode;      /* 0 = auto, 1 = one thread per particle, 2 = lane pairs, 3 = cell tiles  */
-    int32_t reserved[6];
+    int32_t particle_order;    /* scb_particle_order: 0 = SCB_ORDER_RANDOM (default), 1 = SCB_ORDER_CELL; see
+                                  scb_set_particle_order                                              */
+    int32_t reserved[5];
 } scb_options;
 
 /* Per-stage device times of the most recent calls, in milliseconds (CUDA events on the
@@ -202,6 +204,37 @@ SCB_API int scb_step_strided(scb_handle* h, int64_t np, const void* x, const voi
                              void* efield, int mdt, const int64_t n[3], const double min_bounds[3],
                              const double max_bounds[3], const double delta[3], double gamma,
                              int at_cathode, void* ex, void* ey, void* ez);
+
+/* ---- extension: bunches kept ordered by cell ---------------------------------------------------- */
+/* The reference takes particles in whatever order the caller holds them (src/deposition.jl:218-247,
+ * src/interpolation.jl:100-128); with a random order every corner update / corner read is its own 32-byte L2
+ * transaction, which bounds both particle passes far below the HBM roofline.  A tracking loop can keep its bunch
+ * ordered by cell instead: particles move a fraction of a cell per step, so the order decays slowly and a re-sort every
+ * K steps is enough (bench.py reports the break-even K).
+ *
+ * scb_sort_particles computes the permutation that orders the bunch by linear cell index ix + nx*(iy + ny*iz) (the
+ * index arithmetic of deposit!/interpolate_field, clamped to the grid; stable, so particles of one cell keep their
+ * relative order): perm_out[i] = index of the particle that comes i-th, np < 2^31 entries of uint32.
+ * scb_permute applies it to up to 8 per-particle arrays of one element type in one pass: dst[f][i] = src[f][perm[i]]
+ * (dst must not alias src) -- coordinates, charge, momenta, whatever the caller carries.
+ * scb_set_particle_order tells the handle which kernels the particle passes use:
+ *   SCB_ORDER_RANDOM  the sector-transaction-minimising kernels for unordered bunches (default);
+ *   SCB_ORDER_CELL    run-accumulating kernels: every lane walks consecutive particles, keeps the current cell's eight
+ *                     corner sums (deposit) / 24 field values (gather) in registers, warps combine their open runs
+ *                     with a segmented shuffle reduction before touching memory.  Results are correct for ANY order
+ *                     (a cell change merely ends a run); the speed depends on how ordered the bunch is.
+ * scb_particle_order_fraction samples neighbouring particle pairs and returns the fraction that share a cell or sit in
+ * x-adjacent cells (about 1 for an ordered bunch, about 0 for a random one); synchronous. */
+typedef enum scb_particle_order { SCB_ORDER_RANDOM = 0, SCB_ORDER_CELL = 1 } scb_particle_order;
+SCB_API int scb_sort_particles(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
+                               int mdt, const int64_t n[3], const double min_bounds[3], const double delta[3],
+                               uint32_t* perm_out);
+SCB_API int scb_permute(scb_handle* h, int64_t np, const uint32_t* perm, int nfields, const void* const* src,
+                        void* const* dst, int dt);
+SCB_API int scb_set_particle_order(scb_handle* h, int order);
+SCB_API int scb_particle_order_fraction(scb_handle* h, int64_t np, const void* x, const void* y, const void* z,
+                                        int pdt, int mdt, const int64_t n[3], const double min_bounds[3],
+                                        const double delta[3], double* fraction_out);
 
 /* ---- the same step with HOST particle buffers (pinned or pageable) ------------------------ */
 /* Copies x,y,z,q host->device in chunks overlapped with deposition, solves, interpolates in

@@ -24,6 +24,7 @@ from ._lib import LibraryMissing, ScbError  # noqa: F401
 __all__ = ["Mesh3D", "deposit_", "clear_mesh_", "interpolate_field", "solve_", "solve_freespace_",
            "get_green_function_", "cell_indices", "step_", "step_host_", "step_host_async_", "step_host_wait_", "ErrorException", "CLIGHT", "FPEI",
            "solve_potential_", "magnetic_field", "interpolate_kick_",
+           "sort_particles", "permute", "sort_particles_", "set_particle_order", "particle_order_fraction",
            "Handle", "default_handle", "bind_host_to_device"]
 
 CLIGHT = 299792458.0          # src/utils.jl:7
@@ -111,6 +112,11 @@ class Handle:
 
     def drop_green_cache(self):
         self.check(self.lib.scb_drop_green_cache(self.h))
+
+    def set_particle_order(self, order):
+        """``"random"`` (default) or ``"cell"``: which kernels the particle passes use (scb_set_particle_order)."""
+        code = {"random": _lib.SCB_ORDER_RANDOM, "cell": _lib.SCB_ORDER_CELL}.get(order, order)
+        self.check(self.lib.scb_set_particle_order(self.h, int(code)))
 
     def init_comm(self, group):
         """Create the library's own NCCL communicator for `group` (one rank per GPU): rank 0 draws
@@ -432,6 +438,14 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
     q, sq = _particle_view(particles_q, mesh.device, allow_broadcast=True)
     if not (x.dtype == y.dtype == z.dtype == q.dtype):
         raise ErrorException("particle arrays must share one element type")
+    if mesh.group is not None and not mesh.sharded and not clear:
+        # rho already holds a grid summed over the ranks: only THIS call's contribution may be all-reduced
+        # (reducing the whole grid again would count the earlier charge once per rank)
+        from .sharding import allreduce_rho
+        keep = mesh._rho.clone()
+        deposit_(mesh, particles_x, particles_y, particles_z, particles_q, clear=True)   # reduces the new part
+        mesh._rho.add_(keep)
+        return
     if sx == sy == sz == sq == 1:
         hd.check(hd.lib.scb_deposit(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), q.data_ptr(), _tag(x.dtype),
                                     mesh._rho.data_ptr(), mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
@@ -569,11 +583,89 @@ def cell_indices(mesh: Mesh3D, particles_x, particles_y, particles_z):
     return ix, iy, iz
 
 
+# ------------------------------------------------------------------ bunches kept ordered by cell
+def set_particle_order(mesh_or_handle, order) -> None:
+    """Tell the handle how the caller's bunch is ordered: ``"random"`` (default) or ``"cell"`` (the bunch was put in
+    cell order by ``sort_particles_`` and is re-sorted every few steps).  Results do not depend on the setting, only
+    the speed of deposit_ / interpolate_field / step_ does."""
+    hd = mesh_or_handle.handle if isinstance(mesh_or_handle, Mesh3D) else mesh_or_handle
+    hd.set_particle_order(order)
+
+
+def sort_particles(mesh: Mesh3D, particles_x, particles_y, particles_z):
+    """Permutation that orders the bunch by linear cell index of ``mesh`` (scb_sort_particles; stable).  Returns an
+    int32 CUDA tensor ``perm``: ``x[perm.long()]`` is the ordered array (``permute`` does that in one pass)."""
+    torch = _torch()
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    if not (x.dtype == y.dtype == z.dtype):
+        raise ErrorException("particle arrays must share one element type")
+    if not (x.numel() == y.numel() == z.numel()):
+        raise ErrorException("Particle coordinate arrays must have the same length.")
+    perm = torch.empty(x.numel(), dtype=torch.int32, device=x.device)
+    hd.check(hd.lib.scb_sort_particles(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                       mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), perm.data_ptr()))
+    return perm
+
+
+def permute(perm, *arrays, handle: Optional[Handle] = None):
+    """``tuple(a[perm] for a in arrays)`` in passes of up to 8 arrays (scb_permute): 1-D CUDA tensors of one
+    floating-point type and the length of ``perm``."""
+    torch = _torch()
+    if not arrays:
+        return ()
+    hd = handle if handle is not None else default_handle(perm.device.index)
+    hd.use_current_stream()
+    dt = arrays[0].dtype
+    n = perm.numel()
+    for a in arrays:
+        if a.dtype != dt or a.numel() != n or a.device != perm.device or not a.is_contiguous():
+            raise ErrorException("permute: arrays must be contiguous CUDA tensors of one type and the length of perm")
+    outs = [torch.empty_like(a) for a in arrays]
+    for first in range(0, len(arrays), 8):
+        src = arrays[first:first + 8]
+        dst = outs[first:first + 8]
+        sp = (C.c_void_p * len(src))(*[a.data_ptr() for a in src])
+        dp = (C.c_void_p * len(dst))(*[a.data_ptr() for a in dst])
+        hd.check(hd.lib.scb_permute(hd.h, n, perm.data_ptr(), len(src), sp, dp, _tag(dt)))
+    return tuple(outs)
+
+
+def sort_particles_(mesh: Mesh3D, particles_x, particles_y, particles_z, *others):
+    """Order a bunch by cell: returns ``(perm, x, y, z, *others)`` with every array permuted (new tensors)."""
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    perm = sort_particles(mesh, x, y, z)
+    return (perm,) + permute(perm, x, y, z, *[_device_array(a, mesh.device) for a in others], handle=mesh.handle)
+
+
+def particle_order_fraction(mesh: Mesh3D, particles_x, particles_y, particles_z) -> float:
+    """Fraction of sampled neighbouring particle pairs that share a cell or sit in x-adjacent cells
+    (scb_particle_order_fraction): about 1 for a cell-ordered bunch, about 0 for a random one."""
+    hd = mesh.handle
+    hd.use_current_stream()
+    x, y, z = (_device_array(a, mesh.device) for a in (particles_x, particles_y, particles_z))
+    out = C.c_double(0.0)
+    hd.check(hd.lib.scb_particle_order_fraction(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
+                                                mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), C.byref(out)))
+    return float(out.value)
+
+
 def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> None:
     """deposit! + solve! + interpolate_field on device-resident tensors with caller-owned outputs
     (the timed body of benchmark/full_pipeline_benchmark.jl:26-30, without the per-call allocation)."""
+    torch = _torch()
     hd = mesh.handle
     hd.use_current_stream()
+    for t in (x, y, z, q, ex, ey, ez):
+        if not isinstance(t, torch.Tensor) or t.device.type != "cuda" or t.dim() != 1:
+            raise ErrorException("step_ takes 1-D CUDA tensors")
+        if t.dtype != x.dtype:
+            raise ErrorException("particle arrays must share one element type")
+        if t.numel() != x.numel():
+            raise ErrorException("Particle coordinate and charge arrays must have the same length.")
+        if t.device != x.device:
+            raise ErrorException("particle arrays must live on one device")
     st = [t.stride(0) if t.numel() > 1 else 1 for t in (x, y, z, q, ex, ey, ez)]
     if st != [1] * 7:
         if mesh.group is not None:
@@ -609,17 +701,23 @@ def step_(mesh: Mesh3D, x, y, z, q, ex, ey, ez, at_cathode: bool = False) -> Non
 def _host_ptr(a):
     torch = _torch()
     if isinstance(a, torch.Tensor):
-        assert a.device.type == "cpu" and a.is_contiguous()
+        if a.device.type != "cpu" or not a.is_contiguous() or a.dtype not in (torch.float32, torch.float64):
+            raise ErrorException("host-buffer steps take contiguous Float32/Float64 CPU arrays")
         return a.data_ptr(), a.dtype
-    assert a.flags["C_CONTIGUOUS"]
+    if not isinstance(a, np.ndarray) or not a.flags["C_CONTIGUOUS"] or a.dtype not in (np.float32, np.float64):
+        raise ErrorException("host-buffer steps take contiguous Float32/Float64 CPU arrays")
     return a.ctypes.data, (torch.float32 if a.dtype == np.float32 else torch.float64)
 
 
 def _step_host(fn_name, mesh, x, y, z, q, ex, ey, ez, at_cathode):
     hd = mesh.handle
     hd.use_current_stream()
-    (px, dt), (py, _), (pz, _), (pq, _) = (_host_ptr(a) for a in (x, y, z, q))
-    (pex, _), (pey, _), (pez, _) = (_host_ptr(a) for a in (ex, ey, ez))
+    ptrs = [_host_ptr(a) for a in (x, y, z, q, ex, ey, ez)]
+    if any(d != ptrs[0][1] for _, d in ptrs):
+        raise ErrorException("particle arrays must share one element type")
+    if any(len(a) != len(x) for a in (y, z, q, ex, ey, ez)):
+        raise ErrorException("Particle coordinate and charge arrays must have the same length.")
+    (px, dt), (py, _), (pz, _), (pq, _), (pex, _), (pey, _), (pez, _) = ptrs
     if mesh.group is not None:
         # particle shards: every rank feeds its own host shard (scb_step_host_sharded_async)
         hd.init_comm(mesh.group)

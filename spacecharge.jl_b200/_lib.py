@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCB_LIB") or os.path.join(HERE, "lib", "libspacecharge_b200.so")
 
 SCB_F32, SCB_F64 = 0, 1
+SCB_ORDER_RANDOM, SCB_ORDER_CELL = 0, 1
 SCB_OK = 0
 STATUS_NAMES = {0: "SCB_OK", -1: "SCB_ERR_INVALID_ARG", -2: "SCB_ERR_UNSUPPORTED", -3: "SCB_ERR_CUDA",
                 -4: "SCB_ERR_NO_DEVICE", -5: "SCB_ERR_ALLOC", -6: "SCB_ERR_COMM"}
@@ -31,7 +32,8 @@ class ScbError(RuntimeError):
 
 
 class scb_options(C.Structure):
-    _fields_ = [("green_cache", C.c_int32), ("deposit_mode", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("green_cache", C.c_int32), ("deposit_mode", C.c_int32), ("particle_order", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class scb_timing(C.Structure):
@@ -84,6 +86,11 @@ SIGNATURES = {
     "scb_bounds_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _PST, C.c_int, _F64x3, _F64x3]),
     "scb_step_strided": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _PST, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3,
                                    _F64x3, _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
+    "scb_sort_particles": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int, _I64x3, _F64x3, _F64x3, _vp]),
+    "scb_permute": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.c_int]),
+    "scb_set_particle_order": (C.c_int, [_vp, C.c_int]),
+    "scb_particle_order_fraction": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int, _I64x3, _F64x3, _F64x3,
+                                              C.POINTER(C.c_double)]),
     "scb_step_host": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3,
                                 _F64x3, C.c_double, C.c_int, _vp, _vp, _vp]),
     "scb_step_host_async": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3,

@@ -24,6 +24,7 @@ UNITS = {
     "fft_passes_f64.cu": [],
     "green.cu": ["-fmad=false"],
     "particles.cu": ["-fmad=false"],
+    "sorted.cu": ["-fmad=false"],
 }
 
 

@@ -264,6 +264,12 @@ int ensure_packed(scb_handle* h, size_t bytes) {
 int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
                 void* rho, int mdt, const Geom3& g, bool clear, bool cleared_already, const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
+    if (h->opt.particle_order == SCB_ORDER_CELL && !lay) {
+        if (clear && !cleared_already) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)ng * dt_size(mdt), h->stream));
+        SCB_CUDA(h, launch_deposit_runs(pdt, mdt, np, x, y, z, q, rho, g, h->stream));
+        if (np > 0) h->launches += 1;
+        return SCB_OK;
+    }
     int mode = h->opt.deposit_mode;
     if (mode == 0) mode = np >= ng ? 3 : 2;
     if (mode == 3) {
@@ -291,6 +297,11 @@ int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
                     int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready, const Kick& kick = Kick(),
                     const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
+    if (h->opt.particle_order == SCB_ORDER_CELL && !lay && !(packed_ready && *packed_ready)) {
+        SCB_CUDA(h, launch_interpolate_runs(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick));
+        h->launches += 1;
+        return SCB_OK;
+    }
     const bool use_packed = (packed_ready && *packed_ready) || np * 4 >= ng;
     if (!use_packed) {
         SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick, lay));
@@ -983,6 +994,8 @@ int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle
     h->opt.green_cache = 1;
     if (opt) h->opt = *opt;
     if (const char* e = std::getenv("SCB_DEPOSIT_MODE")) h->opt.deposit_mode = std::atoi(e);  // tuning knob
+    if (const char* e = std::getenv("SCB_PARTICLE_ORDER")) h->opt.particle_order = std::atoi(e);
+    if (h->opt.particle_order != SCB_ORDER_CELL) h->opt.particle_order = SCB_ORDER_RANDOM;
     if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
         return SCB_ERR_ALLOC;
@@ -1234,6 +1247,64 @@ int scb_cell_index(scb_handle* h, int64_t np, const void* x, const void* y, cons
     SCB_CUDA(h, launch_cell_index(pdt, mdt, np, x, y, z, make_geom(n1, min_bounds, delta), (long long*)ix,
                                   (long long*)iy, (long long*)iz, h->stream));
     if (np > 0) h->launches += 1;
+    return SCB_OK;
+}
+
+// ---- bunches kept ordered by cell -----------------------------------------------------------------
+int scb_set_particle_order(scb_handle* h, int order) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (order != SCB_ORDER_RANDOM && order != SCB_ORDER_CELL) return fail(h, SCB_ERR_INVALID_ARG, "unknown particle order");
+    h->opt.particle_order = order;
+    return SCB_OK;
+}
+
+int scb_sort_particles(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, int mdt,
+                       const int64_t n[3], const double min_bounds[3], const double delta[3], uint32_t* perm_out) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || np >= (int64_t)1 << 31 || !min_bounds || !delta || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_sort_particles");
+    if (np > 0 && (!x || !y || !z || !perm_out)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    if (np == 0) return SCB_OK;
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    const long long ncell = (long long)n[0] * n[1] * n[2];
+    int key_bits = 1;
+    while (key_bits < 32 && (1ll << key_bits) < ncell) ++key_bits;
+    SCB_TRY(ensure_arena(h, sort_scratch_bytes(np)));
+    SCB_CUDA(h, launch_cell_keys(pdt, mdt, np, x, y, z, make_geom(n, min_bounds, delta), static_cast<unsigned*>(h->arena), h->stream));
+    int launches = 0;
+    SCB_CUDA(h, launch_sort_pairs(h->arena, np, key_bits, perm_out, h->stream, &launches));
+    h->launches += 1 + launches;
+    return SCB_OK;
+}
+
+int scb_permute(scb_handle* h, int64_t np, const uint32_t* perm, int nfields, const void* const* src, void* const* dst, int dt) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || nfields < 0 || nfields > 8 || !valid_dt(dt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_permute");
+    if (np == 0 || nfields == 0) return SCB_OK;
+    if (!perm || !src || !dst) return fail(h, SCB_ERR_INVALID_ARG, "null array");
+    for (int f = 0; f < nfields; ++f)
+        if (!src[f] || !dst[f] || src[f] == dst[f]) return fail(h, SCB_ERR_INVALID_ARG, "scb_permute: null or aliased field");
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_CUDA(h, launch_permute((int)dt_size(dt), np, perm, nfields, src, dst, h->stream));
+    h->launches += 1;
+    return SCB_OK;
+}
+
+int scb_particle_order_fraction(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt, int mdt,
+                                const int64_t n[3], const double min_bounds[3], const double delta[3], double* fraction_out) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (np < 0 || !min_bounds || !delta || !fraction_out || !valid_dt(pdt) || !valid_dt(mdt))
+        return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_particle_order_fraction");
+    if (np > 0 && (!x || !y || !z)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_CUDA(h, launch_order_probe(pdt, mdt, np, x, y, z, make_geom(n, min_bounds, delta), h->d_bounds, h->stream));
+    h->launches += 1;
+    unsigned long long host[2];
+    SCB_CUDA(h, cudaMemcpyAsync(host, h->d_bounds, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    *fraction_out = host[1] ? (double)host[0] / (double)host[1] : 0.0;
     return SCB_OK;
 }
 

@@ -80,6 +80,25 @@ cudaError_t launch_cell_index(int pdt, int mdt, long long np, const void* x, con
 cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, const void* z,
                           double* out6, cudaStream_t s, const PLayout* lay = nullptr);
 
+// sorted.cu -- cell-ordered bunches: keys, radix sort of (key, index), permutation, run-accumulating deposit and gather
+cudaError_t launch_cell_keys(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const Geom3& g,
+                             unsigned* keys, cudaStream_t s, const PLayout* lay = nullptr);
+// scratch layout: [keys0 | keys1 | values | histograms | partials]; the caller fills keys0 (launch_cell_keys)
+size_t sort_scratch_bytes(long long n);
+cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned* perm_out, cudaStream_t s, int* launches);
+cudaError_t launch_permute(int elem_bytes, long long n, const unsigned* perm, int nf, const void* const* src,
+                           void* const* dst, cudaStream_t s);
+// counters2[0] = sampled neighbour pairs in the same or the x-adjacent cell, counters2[1] = sampled pairs
+cudaError_t launch_order_probe(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const Geom3& g,
+                               unsigned long long* counters2, cudaStream_t s);
+// rho must have been cleared (or hold the grid to accumulate into); any particle order is correct
+cudaError_t launch_deposit_runs(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const void* q,
+                                void* rho, const Geom3& g, cudaStream_t s);
+// gathers straight from efield (no node-major copy)
+cudaError_t launch_interpolate_runs(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
+                                    const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,
+                                    const Kick& kick = Kick());
+
 // measurement only: mode 0 = random 256-bit sector reads, mode 1 = random four-lane fp64 sector reductions over
 // `bytes` of `buf`; *ops receives the number of 32-byte sector operations the launch performs
 cudaError_t launch_probe(int mode, void* buf, size_t bytes, int iters, unsigned grid, cudaStream_t s, double* ops);
