@@ -298,7 +298,10 @@ int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
                     const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
     if (h->opt.particle_order == SCB_ORDER_CELL && !lay && !(packed_ready && *packed_ready)) {
-        SCB_CUDA(h, launch_interpolate_runs(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick));
+        // SCB_CELL_GATHER=1 (tuning): one thread per particle straight from efield instead of the run-accumulating walk
+        static const int direct = [] { const char* e = std::getenv("SCB_CELL_GATHER"); return e ? std::atoi(e) : 0; }();
+        if (direct == 1) SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick, nullptr));
+        else SCB_CUDA(h, launch_interpolate_runs(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick));
         h->launches += 1;
         return SCB_OK;
     }
@@ -894,6 +897,7 @@ Geom3 make_geom(const int64_t n[3], const double lo[3], const double delta[3]) {
         g.n[a] = (int)n[a];
         g.lo[a] = lo[a];
         g.delta[a] = delta[a];
+        g.rinv[a] = 1.0 / delta[a];
     }
     return g;
 }
@@ -995,6 +999,7 @@ int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle
     if (opt) h->opt = *opt;
     if (const char* e = std::getenv("SCB_DEPOSIT_MODE")) h->opt.deposit_mode = std::atoi(e);  // tuning knob
     if (const char* e = std::getenv("SCB_PARTICLE_ORDER")) h->opt.particle_order = std::atoi(e);
+    if (const char* e = std::getenv("SCB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));  // experiment
     if (h->opt.particle_order != SCB_ORDER_CELL) h->opt.particle_order = SCB_ORDER_RANDOM;
     if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
@@ -1271,7 +1276,7 @@ int scb_sort_particles(scb_handle* h, int64_t np, const void* x, const void* y, 
     int key_bits = 1;
     while (key_bits < 32 && (1ll << key_bits) < ncell) ++key_bits;
     SCB_TRY(ensure_arena(h, sort_scratch_bytes(np)));
-    SCB_CUDA(h, launch_cell_keys(pdt, mdt, np, x, y, z, make_geom(n, min_bounds, delta), static_cast<unsigned*>(h->arena), h->stream));
+    SCB_CUDA(h, launch_cell_keys(pdt, mdt, np, x, y, z, make_geom(n, min_bounds, delta), h->arena, key_bits, h->stream));
     int launches = 0;
     SCB_CUDA(h, launch_sort_pairs(h->arena, np, key_bits, perm_out, h->stream, &launches));
     h->launches += 1 + launches;

@@ -20,6 +20,7 @@ struct IgfGeom {
 struct Geom3 {
     double lo[3];
     double delta[3];
+    double rinv[3];   // RN(1 / delta), formed on the host (div_exact in particle_common.cuh)
     int n[3];
     int l2_keep = 1;   // 1: grid-side accesses of the particle passes carry an L2 evict_last policy (SCB_L2_HINT=0 disables)
     // gather kernels only: handle the particles whose z cell lies in [zlo, zhi) but not in [exlo, exhi) -- the
@@ -81,9 +82,10 @@ cudaError_t launch_bounds(int pdt, long long np, const void* x, const void* y, c
                           double* out6, cudaStream_t s, const PLayout* lay = nullptr);
 
 // sorted.cu -- cell-ordered bunches: keys, radix sort of (key, index), permutation, run-accumulating deposit and gather
+// scratch layout: [keys0 | keys1 | values | histograms | partials]; launch_cell_keys fills keys0 and the first pass's
+// histogram table, launch_sort_pairs does the rest
 cudaError_t launch_cell_keys(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const Geom3& g,
-                             unsigned* keys, cudaStream_t s, const PLayout* lay = nullptr);
-// scratch layout: [keys0 | keys1 | values | histograms | partials]; the caller fills keys0 (launch_cell_keys)
+                             void* scratch, int key_bits, cudaStream_t s, const PLayout* lay = nullptr);
 size_t sort_scratch_bytes(long long n);
 cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned* perm_out, cudaStream_t s, int* launches);
 cudaError_t launch_permute(int elem_bytes, long long n, const unsigned* perm, int nf, const void* const* src,

@@ -38,24 +38,56 @@ template <typename W> struct CellW {
     W f[3];
 };
 
+// t = a / d, correctly rounded, without the division sequence.  rinv = RN(1/d) comes from the host (a true IEEE
+// division, make_geom).  Markstein's correction steps: with y = RN(1/d) and q a faithful approximation of a/d,
+// RN(q + y * RN(a - q*d)) is the correctly rounded quotient (the residual a - q*d is exact in one FMA).  q0 = RN(a*y)
+// is within 1.5 ulp, q1 within 0.5 ulp + 2^-53 ulp (hence faithful), q2 = RN(a/d) -- bit-identical to the `/` of the
+// reference (src/deposition.jl:39-41, src/interpolation.jl:31-33) for every finite a, at 5 FP64 instructions instead of
+// MUFU.RCP64H + 8 FP64 + range check + slow-path call (ncu, round 2: the cell-ordered particle kernels are bound by
+// instruction issue, not by memory).  tests/test_exact_division.py checks the sequence against exact rational arithmetic.
+__device__ __forceinline__ double div_exact(double a, double d, double rinv) {
+    const double q0 = a * rinv;
+    const double e0 = __fma_rn(-q0, d, a);
+    const double q1 = __fma_rn(e0, rinv, q0);
+    const double e1 = __fma_rn(-q1, d, a);
+    return __fma_rn(e1, rinv, q1);
+}
+__device__ __forceinline__ float div_exact(float a, float d, float) { return __fdiv_rn(a, d); }
+
+__device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
+__device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
+
+// cell index (clamped to [0, n-2]) and fraction along one axis: floor, clamp and fraction as in the reference, with
+// the floor taken by the float -> int conversion (saturating, so the integer clamp equals the clamp of the float value)
+template <typename W>
+__device__ __forceinline__ void locate_axis(W p, const Geom3& g, int a, int& i, W& f) {
+    const W t = div_exact(p - (W)g.lo[a], (W)g.delta[a], (W)g.rinv[a]);
+    i = min(max(floor_to_int(t), 0), g.n[a] - 2);
+    f = t - (W)i;
+}
+
 template <typename W>
 __device__ __forceinline__ void locate(W px, W py, W pz, const Geom3& g, CellW<W>& c) {
-    const W p[3] = {px, py, pz};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const W t = (p[a] - (W)g.lo[a]) / (W)g.delta[a];
-        W fl = floor(t);
-        fl = fmin(fmax(fl, (W)0), (W)(g.n[a] - 2));
-        c.i[a] = (int)fl;
-        c.f[a] = t - fl;
-    }
+    locate_axis<W>(px, g, 0, c.i[0], c.f[0]);
+    locate_axis<W>(py, g, 1, c.i[1], c.f[1]);
+    locate_axis<W>(pz, g, 2, c.i[2], c.f[2]);
 }
 
 // z cell of a particle (same arithmetic as locate) and the slab filter of the gather kernels
 template <typename W> __device__ __forceinline__ bool z_selected(W pz, const Geom3& g) {
-    const W t = (pz - (W)g.lo[2]) / (W)g.delta[2];
-    const int iz = (int)fmin(fmax(floor(t), (W)0), (W)(g.n[2] - 2));
+    int iz;
+    W f;
+    locate_axis<W>(pz, g, 2, iz, f);
     return iz >= g.zlo && iz < g.zhi && !(iz >= g.exlo && iz < g.exhi);
+}
+
+// Result store shared by the gather kernels.  Plain interpolation writes the field value; the fused
+// momentum kick updates the caller's array in place, p <- p + coef * E, with the
+// product and the sum formed separately in W (no contraction: -fmad=false) and rounded to P once.
+template <typename P, typename W>
+__device__ __forceinline__ void put_result(P* __restrict__ arr, long long i, W val, const Kick& k, bool is_z) {
+    if (k.on) val = (W)arr[i] + (W)(is_z ? k.cz : k.cxy) * val;
+    st_stream(arr + i, (P)val);
 }
 
 }  // namespace scb

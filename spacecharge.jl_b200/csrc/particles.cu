@@ -193,15 +193,6 @@ __global__ void __launch_bounds__(256) k_fold_tiles(const T* __restrict__ tiles,
     rho[idx] = accumulate ? rho[idx] + s : s;
 }
 
-// Result store shared by the gather kernels.  Plain interpolation writes the field value; the fused
-// momentum kick updates the caller's array in place, p <- p + coef * E, with the
-// product and the sum formed separately in W (no contraction: -fmad=false) and rounded to P once.
-template <typename P, typename W>
-__device__ __forceinline__ void put_result(P* __restrict__ arr, long long i, W val, const Kick& k, bool is_z) {
-    if (k.on) val = (W)arr[i] + (W)(is_z ? k.cz : k.cxy) * val;
-    st_stream(arr + i, (P)val);
-}
-
 // ---- interpolate: one thread per particle, 24 gathers --------------------------------------
 template <typename P, typename T, bool ST>
 __global__ void __launch_bounds__(256) k_interpolate(long long np, const P* __restrict__ x, const P* __restrict__ y,
@@ -546,9 +537,10 @@ __global__ void k_cell_index(long long np, const P* __restrict__ x, const P* __r
     using W = typename promote<P, T>::type;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
-    ix[i] = (long long)floor(((W)x[i] - (W)g.lo[0]) / (W)g.delta[0]);
-    iy[i] = (long long)floor(((W)y[i] - (W)g.lo[1]) / (W)g.delta[1]);
-    iz[i] = (long long)floor(((W)z[i] - (W)g.lo[2]) / (W)g.delta[2]);
+    // the product kernels' quotient (div_exact), floor unclamped
+    ix[i] = (long long)floor(div_exact((W)x[i] - (W)g.lo[0], (W)g.delta[0], (W)g.rinv[0]));
+    iy[i] = (long long)floor(div_exact((W)y[i] - (W)g.lo[1], (W)g.delta[1], (W)g.rinv[1]));
+    iz[i] = (long long)floor(div_exact((W)z[i] - (W)g.lo[2], (W)g.delta[2], (W)g.rinv[2]));
 }
 
 // ---- extrema -------------------------------------------------------------------------------

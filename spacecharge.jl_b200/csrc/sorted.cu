@@ -27,9 +27,15 @@ namespace scb {
 
 namespace {
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_KPT = 16;                          // keys per thread
-constexpr int SORT_TILE = SORT_THREADS * SORT_KPT;    // 8192 keys per CTA
+#ifndef SCB_SORT_THREADS
+#define SCB_SORT_THREADS 512
+#endif
+constexpr int SORT_THREADS = SCB_SORT_THREADS;
+#ifndef SCB_SORT_KPT
+#define SCB_SORT_KPT 8
+#endif
+constexpr int SORT_KPT = SCB_SORT_KPT;                // keys per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_KPT;    // keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_IPT = 16;
@@ -39,26 +45,50 @@ constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_IPT;   // 4096 counters per CTA
 // ---- cell keys ----------------------------------------------------------------------------------------------------
 // key = linear index of the particle's cell, ix + nx*(iy + ny*iz), from the same locate() as the deposit and the gather
 // (clamped to [0, n-2] per axis), so "sorted by key" is exactly "consecutive particles share cells" for those kernels.
+// One CTA per sort tile: besides the keys it leaves the tile's digit histogram of the FIRST radix pass (hist != nullptr),
+// which saves that pass its own read of the keys.
 template <typename P, typename T, bool ST>
-__global__ void __launch_bounds__(256) k_cell_keys(long long np, const P* __restrict__ x, const P* __restrict__ y,
-                                                    const P* __restrict__ z, const Geom3 g, unsigned* __restrict__ keys,
-                                                    const PLayout L) {
+__global__ void __launch_bounds__(SORT_THREADS) k_cell_keys(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                             const P* __restrict__ z, const Geom3 g, unsigned* __restrict__ keys,
+                                                             const PLayout L, unsigned mask, unsigned* __restrict__ hist,
+                                                             int ntiles) {
     using W = typename promote<P, T>::type;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
-        CellW<W> c;
-        locate<W>((W)ld_stream(x + pidx<ST>(i, L.x)), (W)ld_stream(y + pidx<ST>(i, L.y)),
-                  (W)ld_stream(z + pidx<ST>(i, L.z)), g, c);
-        keys[i] = (unsigned)c.i[0] + (unsigned)g.n[0] * ((unsigned)c.i[1] + (unsigned)g.n[1] * (unsigned)c.i[2]);
+    __shared__ unsigned sh[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) sh[tid] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * SORT_TILE + warp * (SORT_KPT * 32) + lane;
+#pragma unroll 2
+    for (int r = 0; r < SORT_KPT; ++r) {
+        const long long i = base + r * 32;
+        unsigned d = 0xffffffffu;
+        if (i < np) {
+            CellW<W> c;
+            locate<W>((W)ld_stream(x + pidx<ST>(i, L.x)), (W)ld_stream(y + pidx<ST>(i, L.y)),
+                      (W)ld_stream(z + pidx<ST>(i, L.z)), g, c);
+            const unsigned key = (unsigned)c.i[0] + (unsigned)g.n[0] * ((unsigned)c.i[1] + (unsigned)g.n[1] * (unsigned)c.i[2]);
+            keys[i] = key;
+            d = key & mask;
+        }
+        if (hist) {
+            const unsigned d0 = __shfl_sync(FULL, d, 0);
+            if (__all_sync(FULL, d == d0)) {
+                if (lane == 0 && d0 != 0xffffffffu) atomicAdd(&sh[d0], 32u);
+            } else if (d != 0xffffffffu) {
+                atomicAdd(&sh[d], 1u);
+            }
+        }
     }
+    __syncthreads();
+    if (hist && (unsigned)tid <= mask) hist[(size_t)tid * ntiles + blockIdx.x] = sh[tid];
 }
 
 // ---- LSD radix sort of (key, index) pairs, 32-bit keys, up to 8 bits per pass -------------------------------------
 // Three kernels per pass: per-tile digit histograms (digit-major, so that ONE exclusive scan over the whole table
 // yields every tile's global base per digit), the scan, and the scatter.  Ranks inside a tile come from
 // __match_any_sync on the digit (cost independent of the digit distribution: a bunch that is already almost sorted --
-// the common case in a tracking loop -- has one digit value per tile in the last pass).  A warp owns 512 consecutive
-// keys of the tile and walks them in 16 rounds of 32, so (warp, round, lane) order = index order and the sort is stable.
+// the common case in a tracking loop -- has one digit value per tile in the last pass).  A warp owns 32 * SORT_KPT consecutive
+// keys of the tile and walks them in SORT_KPT rounds of 32, so (warp, round, lane) order = index order and the sort is stable.
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const unsigned* __restrict__ keys, long long n, int shift,
                                                               unsigned mask, unsigned* __restrict__ hist, int ntiles) {
     __shared__ unsigned sh[256];
@@ -66,13 +96,24 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const unsigned* __r
     if (tid < 256) sh[tid] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * SORT_TILE + warp * (SORT_KPT * 32) + lane;
+    // all 16 keys first (independent loads), then the counting: one vote per round catches the case that bounds shared
+    // atomics (every lane on the same counter -- the last pass of an almost ordered bunch), everything else goes through
+    // native integer atomics (the match-based count of the first version made this kernel latency-bound: 0.60 ms for
+    // 0.4 GB)
+    unsigned d[SORT_KPT];
 #pragma unroll
     for (int r = 0; r < SORT_KPT; ++r) {
         const long long i = base + r * 32;
-        const bool valid = i < n;
-        const unsigned d = valid ? ((__ldg(keys + i) >> shift) & mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(FULL, d);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[d], (unsigned)__popc(peers));
+        d[r] = i < n ? ((__ldg(keys + i) >> shift) & mask) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < SORT_KPT; ++r) {
+        const unsigned d0 = __shfl_sync(FULL, d[r], 0);
+        if (__all_sync(FULL, d[r] == d0)) {
+            if (lane == 0 && d0 != 0xffffffffu) atomicAdd(&sh[d0], 32u);
+        } else if (d[r] != 0xffffffffu) {
+            atomicAdd(&sh[d[r]], 1u);
+        }
     }
     __syncthreads();
     if ((unsigned)tid <= mask) hist[(size_t)tid * ntiles + blockIdx.x] = sh[tid];
@@ -153,7 +194,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(unsigned* __restric
 
 // vals_in == nullptr: the values are the key indices themselves (first pass); keys_out == nullptr: the ordered keys are
 // not needed (last pass)
-__global__ void __launch_bounds__(SORT_THREADS, 2) k_radix_scatter(const unsigned* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, 1024 / SORT_THREADS) k_radix_scatter(const unsigned* __restrict__ keys_in,
                                                                     const unsigned* __restrict__ vals_in,
                                                                     unsigned* __restrict__ keys_out,
                                                                     unsigned* __restrict__ vals_out, long long n, int shift,
@@ -181,21 +222,26 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_radix_scatter(const unsigne
     }
     __syncthreads();
     unsigned* wh = whist + warp * 256;
+    // rank of every key among the warp's keys with the same digit, in (round, lane) order.  The 16 match operations are
+    // independent and issue back to back; the per-digit running counts then advance with one returning shared-memory
+    // atomic per round and distinct digit (issued by the first lane of each group of equal digits), and the old values
+    // reach the other lanes of the group with one shuffle per round.
+    unsigned info[SORT_KPT];   // leader | rank inside the round << 5 | group size << 10
+#pragma unroll
+    for (int r = 0; r < SORT_KPT; ++r) {
+        const unsigned peers = __match_any_sync(FULL, (k[r] >> shift) & mask);
+        info[r] = (unsigned)(__ffs(peers) - 1) | ((unsigned)__popc(peers & ((1u << lane) - 1u)) << 5) |
+                  ((unsigned)__popc(peers) << 10);
+    }
     unsigned rk[SORT_KPT];
 #pragma unroll
     for (int r = 0; r < SORT_KPT; ++r) {
-        const unsigned d = (k[r] >> shift) & mask;
-        const unsigned peers = __match_any_sync(FULL, d);
-        const int leader = __ffs(peers) - 1;
-        unsigned old = 0;
-        if (lane == leader) {
-            old = wh[d];
-            wh[d] = old + (unsigned)__popc(peers);
-        }
-        old = __shfl_sync(FULL, old, leader);
-        rk[r] = old + (unsigned)__popc(peers & ((1u << lane) - 1u));
-        __syncwarp();
+        rk[r] = 0;
+        if ((info[r] & 31u) == (unsigned)lane) rk[r] = atomicAdd(&wh[(k[r] >> shift) & mask], info[r] >> 10);
+        __syncwarp();   // orders this round's atomics before the next round's (ranks must follow the round order)
     }
+#pragma unroll
+    for (int r = 0; r < SORT_KPT; ++r) rk[r] = __shfl_sync(FULL, rk[r], info[r] & 31u) + ((info[r] >> 5) & 31u);
     __syncthreads();
     // per digit: exclusive prefix over the warps, total of the tile
     unsigned total = 0;
@@ -297,6 +343,18 @@ __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
 }
+__device__ __forceinline__ void ld4(const double* p, double (&v)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+__device__ __forceinline__ void ld4(const float* p, float (&v)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[2]) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[2]) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+}
 __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
@@ -320,8 +378,34 @@ __device__ __forceinline__ void flush_run(T* __restrict__ rho, int cell, const W
     red_add_hint(r + sz + sy + 1, (T)s[7], pol);
 }
 
-// VEC: all four arrays are 32-byte aligned (256-bit loads); otherwise element loads.  counters (optional):
-// [0] += number of flushes (runs) -- the launcher's measure of how ordered the bunch was.
+// one lane's walk over its (up to) 8 consecutive particles: the corner sums of the current cell stay in s[], a cell
+// change sends them to rho.  ALL: every one of the 8 exists (no per-particle bound checks).
+template <typename P, typename T, typename W, bool ALL>
+__device__ __forceinline__ void walk_deposit(const P (&px)[8], const P (&py)[8], const P (&pz)[8], const P (&pq)[8], int cnt,
+                                             const Geom3& g, T* __restrict__ rho, long long sy, long long sz,
+                                             unsigned long long pol, int& cur, W (&s)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (ALL || j < cnt) {
+            CellW<W> c;
+            locate<W>((W)px[j], (W)py[j], (W)pz[j], g, c);
+            const int cell = c.i[0] + (int)sy * c.i[1] + (int)sz * c.i[2];
+            const W one = (W)1, charge = (W)pq[j];
+            const W qx0 = charge * (one - c.f[0]), qx1 = charge * c.f[0];              // charge * w_x
+            const W wy0 = one - c.f[1], wy1 = c.f[1], wz0 = one - c.f[2], wz1 = c.f[2];
+            const W qxy00 = qx0 * wy0, qxy10 = qx1 * wy0, qxy01 = qx0 * wy1, qxy11 = qx1 * wy1;   // * w_y
+            const W v[8] = {qxy00 * wz0, qxy10 * wz0, qxy01 * wz0, qxy11 * wz0,
+                            qxy00 * wz1, qxy10 * wz1, qxy01 * wz1, qxy11 * wz1};       // ((q*wx)*wy)*wz
+            const bool same = cell == cur;
+            if (!same && cur >= 0) flush_run<T, W>(rho, cur, s, sy, sz, pol);
+            cur = cell;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = (same ? s[k] : (W)0) + v[k];
+        }
+    }
+}
+
+// VEC: all four arrays are 32-byte aligned (256-bit loads); otherwise element loads.
 template <typename P, typename T, bool VEC>
 __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                           const P* __restrict__ z, const P* __restrict__ q,
@@ -334,9 +418,10 @@ __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* 
     const unsigned long long pol = l2_policy(g.l2_keep);
     for (long long wbase = warp * 256; wbase < np; wbase += nwarps * 256) {
         const long long i0 = wbase + lane * 8;
+        const bool full = wbase + 256 <= np;   // warp-uniform
         const int cnt = (int)(np - i0 >= 8 ? 8 : (np - i0 > 0 ? np - i0 : 0));
         P px[8], py[8], pz[8], pq[8];
-        if (VEC && cnt == 8) {
+        if (VEC && full) {
             ld8(x + i0, px);
             ld8(y + i0, py);
             ld8(z + i0, pz);
@@ -355,29 +440,8 @@ __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* 
         W s[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = (W)0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < cnt) {
-                CellW<W> c;
-                locate<W>((W)px[j], (W)py[j], (W)pz[j], g, c);
-                const int cell = c.i[0] + (int)sy * c.i[1] + (int)sz * c.i[2];
-                const W one = (W)1, charge = (W)pq[j];
-                const W qx0 = charge * (one - c.f[0]), qx1 = charge * c.f[0];              // charge * w_x
-                const W wy0 = one - c.f[1], wy1 = c.f[1], wz0 = one - c.f[2], wz1 = c.f[2];
-                const W qxy00 = qx0 * wy0, qxy10 = qx1 * wy0, qxy01 = qx0 * wy1, qxy11 = qx1 * wy1;   // * w_y
-                const W v[8] = {qxy00 * wz0, qxy10 * wz0, qxy01 * wz0, qxy11 * wz0,
-                                qxy00 * wz1, qxy10 * wz1, qxy01 * wz1, qxy11 * wz1};       // ((q*wx)*wy)*wz
-                if (cell == cur) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) s[k] += v[k];
-                } else {
-                    if (cur >= 0) flush_run<T, W>(rho, cur, s, sy, sz, pol);
-                    cur = cell;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) s[k] = v[k];
-                }
-            }
-        }
+        if (full) walk_deposit<P, T, W, true>(px, py, pz, pq, 8, g, rho, sy, sz, pol, cur, s);
+        else walk_deposit<P, T, W, false>(px, py, pz, pq, cnt, g, rho, sy, sz, pol, cur, s);
         // the lanes' open runs: adjacent lanes with the same cell form a segment; inclusive segmented scan, the last
         // lane of every segment holds its sum
         const int prev = __shfl_up_sync(FULL, cur, 1), next = __shfl_down_sync(FULL, cur, 1);
@@ -389,7 +453,7 @@ __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* 
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const W t = __shfl_up_sync(FULL, s[k], o);
-                if (take) s[k] += t;
+                s[k] += take ? t : (W)0;
             }
         }
         if (cur >= 0 && (lane == 31 || next != cur)) flush_run<T, W>(rho, cur, s, sy, sz, pol);
@@ -400,101 +464,125 @@ __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* 
 // Every lane walks 4 consecutive particles; the 24 field values of the current cell stay in registers while the cell
 // does not change.  Weights, products and the left-to-right sum are those of src/interpolation.jl:46-85 (bit-identical
 // to k_interpolate).  Results leave as one 256-bit (Float64) / 128-bit (Float32) store per component.
+// tuning (build.py -D ...): particles per lane (4 or 2), CTA size, minimum resident CTAs, results stored one by one
+#ifndef SCB_GR_M
+#define SCB_GR_M 4
+#endif
+// measured at 1e8 particles / 256^3 Float64, cell-ordered (profiles/r02_ab_gather_runs.log): 256 threads x 2 CTAs (128
+// registers, 428 bytes spilled) 1.38 ms; 128 threads x 3 CTAs (168 registers) 1.21 ms; 2 particles per lane 1.77 ms;
+// element stores as results are formed 2.05 ms (partial-sector writes); one thread per particle from L1 1.60 ms
+#ifndef SCB_GR_THREADS
+#define SCB_GR_THREADS 128
+#endif
+#ifndef SCB_GR_MINB
+#define SCB_GR_MINB 3
+#endif
+#ifndef SCB_GR_STORE_NOW
+#define SCB_GR_STORE_NOW 0
+#endif
+constexpr int GR_M = SCB_GR_M;
+
+// ALL: every one of the lane's GR_M particles exists.  NOW: results are stored as they are formed (element stores)
+// instead of being kept for one vector store per component.
+template <typename P, typename T, typename W, bool ALL, bool NOW>
+__device__ __forceinline__ void walk_gather(const P (&px)[GR_M], const P (&py)[GR_M], const P (&pz)[GR_M], int cnt,
+                                            const Geom3& g, const T* __restrict__ e, long long sy, long long sz,
+                                            long long sc, P (&ox)[GR_M], P (&oy)[GR_M], P (&oz)[GR_M], const Kick& kick,
+                                            P* __restrict__ ex, P* __restrict__ ey, P* __restrict__ ez) {
+    int cur = -1;
+    T n[3][8];
+#pragma unroll
+    for (int j = 0; j < GR_M; ++j) {
+        if (!NOW) ox[j] = oy[j] = oz[j] = (P)0;
+        if (ALL || j < cnt) {
+            CellW<W> c;
+            locate<W>((W)px[j], (W)py[j], (W)pz[j], g, c);
+            const int cell = c.i[0] + (int)sy * c.i[1] + (int)sz * c.i[2];
+            if (cell != cur) {
+                cur = cell;
+                const T* b = e + cell;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const T* bk = b + k * sc;
+                    n[k][0] = __ldg(bk);
+                    n[k][1] = __ldg(bk + 1);
+                    n[k][2] = __ldg(bk + sy);
+                    n[k][3] = __ldg(bk + sy + 1);
+                    n[k][4] = __ldg(bk + sz);
+                    n[k][5] = __ldg(bk + sz + 1);
+                    n[k][6] = __ldg(bk + sz + sy);
+                    n[k][7] = __ldg(bk + sz + sy + 1);
+                }
+            }
+            const W dx = c.f[0], dy = c.f[1], dz = c.f[2], one = (W)1;
+            // src/interpolation.jl:46-53
+            const W w000 = (one - dx) * (one - dy) * (one - dz);
+            const W w100 = dx * (one - dy) * (one - dz);
+            const W w010 = (one - dx) * dy * (one - dz);
+            const W w110 = dx * dy * (one - dz);
+            const W w001 = (one - dx) * (one - dy) * dz;
+            const W w101 = dx * (one - dy) * dz;
+            const W w011 = (one - dx) * dy * dz;
+            const W w111 = dx * dy * dz;
+            W out[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)   // src/interpolation.jl:56-85, left-to-right sum
+                out[k] = (W)n[k][0] * w000 + (W)n[k][1] * w100 + (W)n[k][2] * w010 + (W)n[k][3] * w110 +
+                         (W)n[k][4] * w001 + (W)n[k][5] * w101 + (W)n[k][6] * w011 + (W)n[k][7] * w111;
+            if (NOW) {
+                put_result<P, W>(ex, j, out[0], kick, false);
+                put_result<P, W>(ey, j, out[1], kick, false);
+                put_result<P, W>(ez, j, out[2], kick, true);
+            } else {
+                ox[j] = (P)out[0];
+                oy[j] = (P)out[1];
+                oz[j] = (P)out[2];
+            }
+        }
+    }
+}
+
 template <typename P, typename T, bool VEC>
-__global__ void __launch_bounds__(256, 2) k_interpolate_runs(long long np, const P* __restrict__ x, const P* __restrict__ y,
+__global__ void __launch_bounds__(SCB_GR_THREADS, SCB_GR_MINB) k_interpolate_runs(long long np, const P* __restrict__ x, const P* __restrict__ y,
                                                               const P* __restrict__ z, const T* __restrict__ e,
                                                               const Geom3 g, P* __restrict__ ex, P* __restrict__ ey,
                                                               P* __restrict__ ez, const Kick kick) {
     using W = typename promote<P, T>::type;
+    constexpr int PER_WARP = 32 * GR_M;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1], sc = sz * g.n[2];
-    for (long long wbase = warp * 128; wbase < np; wbase += nwarps * 128) {
-        const long long i0 = wbase + lane * 4;
-        const int cnt = (int)(np - i0 >= 4 ? 4 : (np - i0 > 0 ? np - i0 : 0));
-        P px[4], py[4], pz[4];
-        if (VEC && cnt == 4) {
+    for (long long wbase = warp * PER_WARP; wbase < np; wbase += nwarps * PER_WARP) {
+        const long long i0 = wbase + lane * GR_M;
+        const bool full = wbase + PER_WARP <= np;   // warp-uniform
+        const int cnt = (int)(np - i0 >= GR_M ? GR_M : (np - i0 > 0 ? np - i0 : 0));
+        P px[GR_M], py[GR_M], pz[GR_M];
+        if (VEC && full) {
             ld4(x + i0, px);
             ld4(y + i0, py);
             ld4(z + i0, pz);
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < GR_M; ++j) {
                 const bool ok = j < cnt;
                 px[j] = ok ? ld_stream(x + i0 + j) : (P)0;
                 py[j] = ok ? ld_stream(y + i0 + j) : (P)0;
                 pz[j] = ok ? ld_stream(z + i0 + j) : (P)0;
             }
         }
-        int cur = -1;
-        T n[3][8];
-        P ox[4], oy[4], oz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            ox[j] = oy[j] = oz[j] = (P)0;
-            if (j < cnt) {
-                CellW<W> c;
-                locate<W>((W)px[j], (W)py[j], (W)pz[j], g, c);
-                const int cell = c.i[0] + (int)sy * c.i[1] + (int)sz * c.i[2];
-                if (cell != cur) {
-                    cur = cell;
-                    const T* b = e + cell;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const T* bk = b + k * sc;
-                        n[k][0] = __ldg(bk);
-                        n[k][1] = __ldg(bk + 1);
-                        n[k][2] = __ldg(bk + sy);
-                        n[k][3] = __ldg(bk + sy + 1);
-                        n[k][4] = __ldg(bk + sz);
-                        n[k][5] = __ldg(bk + sz + 1);
-                        n[k][6] = __ldg(bk + sz + sy);
-                        n[k][7] = __ldg(bk + sz + sy + 1);
-                    }
-                }
-                const W dx = c.f[0], dy = c.f[1], dz = c.f[2], one = (W)1;
-                // src/interpolation.jl:46-53
-                const W w000 = (one - dx) * (one - dy) * (one - dz);
-                const W w100 = dx * (one - dy) * (one - dz);
-                const W w010 = (one - dx) * dy * (one - dz);
-                const W w110 = dx * dy * (one - dz);
-                const W w001 = (one - dx) * (one - dy) * dz;
-                const W w101 = dx * (one - dy) * dz;
-                const W w011 = (one - dx) * dy * dz;
-                const W w111 = dx * dy * dz;
-                W out[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k)   // src/interpolation.jl:56-85, left-to-right sum
-                    out[k] = (W)n[k][0] * w000 + (W)n[k][1] * w100 + (W)n[k][2] * w010 + (W)n[k][3] * w110 +
-                             (W)n[k][4] * w001 + (W)n[k][5] * w101 + (W)n[k][6] * w011 + (W)n[k][7] * w111;
-                ox[j] = (P)out[0];
-                oy[j] = (P)out[1];
-                oz[j] = (P)out[2];
+        P ox[GR_M], oy[GR_M], oz[GR_M];
+        constexpr bool NOW = SCB_GR_STORE_NOW != 0;
+        if (VEC && full && !kick.on) {
+            walk_gather<P, T, W, true, NOW>(px, py, pz, GR_M, g, e, sy, sz, sc, ox, oy, oz, kick, ex + i0, ey + i0, ez + i0);
+            if (!NOW) {
+                st4(ex + i0, ox);
+                st4(ey + i0, oy);
+                st4(ez + i0, oz);
             }
-        }
-        if (kick.on) {
-            // fused momentum kick: p <- p + coef * E, product and sum formed separately in W, rounded to P once
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < cnt) {
-                    ox[j] = (P)((W)ex[i0 + j] + (W)kick.cxy * (W)ox[j]);
-                    oy[j] = (P)((W)ey[i0 + j] + (W)kick.cxy * (W)oy[j]);
-                    oz[j] = (P)((W)ez[i0 + j] + (W)kick.cz * (W)oz[j]);
-                }
-        }
-        if (VEC && cnt == 4) {
-            st4(ex + i0, ox);
-            st4(ey + i0, oy);
-            st4(ez + i0, oz);
         } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < cnt) {
-                    st_stream(ex + i0 + j, ox[j]);
-                    st_stream(ey + i0 + j, oy[j]);
-                    st_stream(ez + i0 + j, oz[j]);
-                }
+            // tail of the bunch, unaligned arrays, fused momentum kick (p <- p + coef * E): element stores
+            walk_gather<P, T, W, false, true>(px, py, pz, cnt, g, e, sy, sz, sc, ox, oy, oz, kick, ex + i0, ey + i0, ez + i0);
         }
     }
 }
@@ -523,13 +611,25 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+static inline int sort_digit_bits(int key_bits) {
+    if (key_bits < 1) key_bits = 1;
+    const int passes = (key_bits + 7) / 8;
+    return (key_bits + passes - 1) / passes;
+}
+
+// scratch: the sort scratch of launch_sort_pairs (sort_scratch_bytes); fills its first key buffer and the histogram table
+// of the first pass
 cudaError_t launch_cell_keys(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const Geom3& g,
-                             unsigned* keys, cudaStream_t s, const PLayout* lay) {
+                             void* scratch, int key_bits, cudaStream_t s, const PLayout* lay) {
     if (np <= 0) return cudaSuccess;
-    const unsigned grid = capped_grid(np, 256, 64);
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const int ntiles = (int)((np + SORT_TILE - 1) / SORT_TILE);
+    unsigned* keys = static_cast<unsigned*>(scratch);
+    unsigned* hist = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + 3 * up((size_t)np * 4));
+    const unsigned mask = (1u << sort_digit_bits(key_bits)) - 1u;
 #define CALL(P, T)                                                                                                        \
-    if (lay) k_cell_keys<P, T, true><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, g, keys, *lay);       \
-    else k_cell_keys<P, T, false><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, g, keys, PLayout{});
+    if (lay) k_cell_keys<P, T, true><<<ntiles, SORT_THREADS, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, g, keys, *lay, mask, hist, ntiles); \
+    else k_cell_keys<P, T, false><<<ntiles, SORT_THREADS, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, g, keys, PLayout{}, mask, hist, ntiles);
     SCB_DISPATCH_PT(CALL)
 #undef CALL
     return cudaGetLastError();
@@ -544,8 +644,8 @@ size_t sort_scratch_bytes(long long n) {
     return 3 * up((size_t)n * 4) + up((size_t)nh * 4) + up((size_t)nparts * 4);
 }
 
-// orders the indices 0..n-1 by key (stable); keys0 = scratch (first key buffer, filled by the caller with the keys).
-// perm_out receives the permutation.  `key_bits` significant bits.  Returns the number of kernel launches in *launches.
+// orders the indices 0..n-1 by key (stable); the first key buffer and the first pass's histogram table inside `scratch`
+// come from launch_cell_keys.  perm_out receives the permutation.  `key_bits` significant bits.  *launches: kernel count.
 cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned* perm_out, cudaStream_t s, int* launches) {
     if (launches) *launches = 0;
     if (n <= 0) return cudaSuccess;
@@ -559,7 +659,7 @@ cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned
     unsigned* partial = reinterpret_cast<unsigned*>(base + 3 * up((size_t)n * 4) + up((size_t)nh_max * 4));
     if (key_bits < 1) key_bits = 1;
     const int passes = (key_bits + 7) / 8;
-    const int bits = (key_bits + passes - 1) / passes;
+    const int bits = sort_digit_bits(key_bits);
     static bool attr_set = false;
     const size_t smem = (size_t)(2 * SORT_TILE + SORT_WARPS * 256 + 512) * 4;
     if (!attr_set) {
@@ -580,12 +680,12 @@ cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned
         unsigned* kout = p == passes - 1 ? nullptr : keys[(p + 1) & 1];
         const unsigned* vin = p == 0 ? nullptr : vbuf[(p - 1) & 1];
         unsigned* vout = vbuf[p & 1];
-        k_radix_hist<<<ntiles, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, ntiles);
+        if (p > 0) k_radix_hist<<<ntiles, SORT_THREADS, 0, s>>>(kin, n, shift, mask, hist, ntiles);
         k_scan_reduce<<<nparts, SCAN_THREADS, 0, s>>>(hist, nh, partial);
         k_scan_top<<<1, 1024, 0, s>>>(partial, nparts);
         k_scan_apply<<<nparts, SCAN_THREADS, 0, s>>>(hist, nh, partial);
         k_radix_scatter<<<ntiles, SORT_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, mask, hist, ntiles);
-        if (launches) *launches += 5;
+        if (launches) *launches += p > 0 ? 5 : 4;
     }
     return cudaGetLastError();
 }
@@ -637,11 +737,11 @@ cudaError_t launch_interpolate_runs(int pdt, int mdt, long long np, const void* 
                                     const Kick& kick) {
     if (np <= 0) return cudaSuccess;
     static const int per_sm = env_int("SCB_RUNS_PER_SM", 64);
-    const unsigned grid = capped_grid(np, 256 * 4, per_sm);
+    const unsigned grid = capped_grid(np, SCB_GR_THREADS * GR_M, per_sm * 256 / SCB_GR_THREADS);
     const bool vec = aligned32(x, y, z, ex) && aligned32(ey, ez, ey, ez);
 #define CALL(P, T)                                                                                                         \
-    if (vec) k_interpolate_runs<P, T, true><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick); \
-    else k_interpolate_runs<P, T, false><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick);
+    if (vec) k_interpolate_runs<P, T, true><<<grid, SCB_GR_THREADS, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick); \
+    else k_interpolate_runs<P, T, false><<<grid, SCB_GR_THREADS, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const T*)efield, g, (P*)ex, (P*)ey, (P*)ez, kick);
     SCB_DISPATCH_PT(CALL)
 #undef CALL
     return cudaGetLastError();
