@@ -36,6 +36,7 @@ WORKLOADS = {
 SIGMA, QTOT = 1.0e-3, 1.0e-9
 STAGE_REPS = 10            # repetitions behind the per-stage minimum / median
 NOMINAL_HBM_GBS = 8000.0   # HBM3e nominal; the roofline denominator is the MEASURED copy bandwidth, this one is reported beside it
+NVLINK_GBS = 770.0         # measured peer copy per direction and GPU (B200_PROFILING.md); nominal 900
 
 
 def measured_peak():
@@ -121,43 +122,174 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=150.0):
-    """The reference's CPU structure on the host cores.  One step = the full-grid solve plus
-    deposit/interpolate on a bounded particle sample, particle time scaled to the full count."""
+def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=170.0):
+    """The reference's CPU structure on the host cores.  One step = the full-grid solve plus deposit/interpolate on a
+    bounded particle sample; the particle passes are then measured ONCE on all particles, and `value` uses that
+    measurement (no extrapolation) next to the mean solve time."""
     from oracle import spacecharge_oracle as so
     from oracle.cpu_reference import RefPort
 
     cores = os.cpu_count() or 1
+    t_begin = time.perf_counter()
     nsample = min(npart, 4_000_000)
     rng = np.random.default_rng(42)
     x, y, z = (rng.standard_normal(nsample) * SIGMA for _ in range(3))
     z = z + zshift * SIGMA
     q = np.full(nsample, QTOT / npart)
     mesh = so.mesh_from_particles(grid, x, y, z)
+    # the thread count is set explicitly (omp_set_num_threads + pocketfft workers): torchrun exports OMP_NUM_THREADS=1
     rp = RefPort(grid, mesh.min_bounds, mesh.delta, 1.0, threads=cores)
-    scale = npart / nsample
-    times, parts = [], []
-    t_begin = time.perf_counter()
-    done = 0
-    for it in range(warmup + steps):
+    # every step = the full-grid solve + the particle passes on the bounded sample; the step count follows
+    # --steps / --warmup unless the wall budget runs out first (the solve alone is ~9 s at config 5 on 16 cores)
+    parts = []
+    n_warm, n_timed, planned = 0, 0, None
+    while True:
         _, t = rp.timed_step(x, y, z, q, at_cathode, mesh.max_bounds)
-        if it >= min(warmup, 1) or steps == 0:
-            times.append(t["solve_s"] + scale * (t["deposit_s"] + t["interpolate_s"]))
+        if planned is None:
+            t1 = max(time.perf_counter() - t_begin, 1e-3)
+            fit = max(1, int(budget_s / (t["deposit_s"] + t["solve_s"] + t["interpolate_s"])) - (1 if npart > nsample else 0))
+            want_w, want_s = warmup, max(steps, 1)
+            if want_w + want_s > fit:   # drop warm-up steps first, then timed steps
+                want_w = min(want_w, max(0, fit // 5))
+                want_s = max(1, min(want_s, fit - want_w))
+            planned = (want_w, want_s)
+        if n_warm < planned[0]:
+            n_warm += 1
+        else:
             parts.append(t)
-            done += 1
-        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            n_timed += 1
+        if n_timed >= planned[1]:
             break
-    t_step = float(np.mean(times))
-    last = parts[-1]
+    solve_s = float(np.mean([p["solve_s"] for p in parts]))
+    dep_s = float(np.mean([p["deposit_s"] for p in parts]))
+    int_s = float(np.mean([p["interpolate_s"] for p in parts]))
+    scale = npart / nsample
+    full = None
+    if npart > nsample:
+        # the particle passes ONCE on all particles of the workload (same mesh, same field): the measured value the
+        # scaled sample times stand for
+        del x, y, z, q
+        fx, fy, fz = (rng.standard_normal(npart) * SIGMA for _ in range(3))
+        fz += zshift * SIGMA
+        for a, lo, hi in zip((fx, fy, fz), mesh.min_bounds, mesh.max_bounds):   # keep the sample's mesh geometry
+            np.clip(a, float(lo), float(hi) - 1e-12 * abs(float(hi)), out=a)
+        fq = np.full(npart, QTOT / npart)
+        t0 = time.perf_counter()
+        rp.deposit(fx, fy, fz, fq)
+        t1 = time.perf_counter()
+        rp.interpolate(fx, fy, fz)
+        t2 = time.perf_counter()
+        full = {"deposit_s": t1 - t0, "interpolate_s": t2 - t1}
+        del fx, fy, fz, fq
+    dep_full = full["deposit_s"] if full else dep_s
+    int_full = full["interpolate_s"] if full else int_s
+    t_step = solve_s + dep_full + int_full
     return {
         "value": npart / t_step, "unit": "particles/s", "cores": cores, "kind": "port",
-        "sample": ("full %dx%dx%d solve + deposit/interpolate of %d of %d particles, particle time scaled x%.0f; "
-                   "C restatement of the reference structure + scipy/pocketfft C2C (FFTW absent); %d step(s) timed"
-                   % (grid + (nsample, npart, scale, done))),
+        "sample": ("per step: full %dx%dx%d solve + deposit/interpolate of a %d-particle sample (measured %.0f ms per step, "
+                   "unscaled); deposit + interpolate of all %d particles measured once (%s); value = particles / (mean solve "
+                   "+ full-bunch particle passes); C restatement of the reference structure, OpenMP threads %d + "
+                   "scipy/pocketfft C2C workers %d (FFTW absent); %d warm-up + %d timed step(s) of %d + %d requested"
+                   % (grid + (nsample, 1e3 * (solve_s + dep_s + int_s), npart,
+                              "%.0f + %.0f ms; the scaled sample gives %.0f + %.0f ms" % (
+                                  1e3 * dep_full, 1e3 * int_full, 1e3 * scale * dep_s, 1e3 * scale * int_s) if full else "= the sample",
+                              rp.omp_threads, cores, n_warm, n_timed, warmup, steps))),
         "ms_per_step": 1e3 * t_step,
-        "stages_ms": {"deposit": 1e3 * scale * last["deposit_s"], "solve": 1e3 * last["solve_s"],
-                      "interpolate": 1e3 * scale * last["interpolate_s"]},
-        "steps_timed": done,
+        "sample_ms_per_step": 1e3 * (solve_s + dep_s + int_s),
+        "stages_ms": {"deposit": 1e3 * dep_full, "solve": 1e3 * solve_s, "interpolate": 1e3 * int_full},
+        "steps_timed": n_timed, "warmup_done": n_warm, "wall_s": time.perf_counter() - t_begin,
+    }
+
+
+def cell_ordered_regime(scb, mesh, x, y, z, q, ex, ey, ez, at_cathode, stage_random, n_local, grid, s, world, barrier, peak):
+    """Times the step on the bunch ordered by cell (scb_sort_particles + scb_permute, SCB_ORDER_CELL kernels).
+
+    All times are device times of this rank (CUDA events); in a particle-sharded run every rank orders its own shard."""
+    import torch
+
+    hd = mesh.handle
+
+    def timed(fn, reps=3):
+        best, out = None, None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            best = ms if best is None else min(best, ms)
+        return best, out
+
+    def stage_times(px, py, pz, pq, reps=5):
+        for _ in range(2):
+            scb.step_(mesh, px, py, pz, pq, ex, ey, ez, at_cathode=at_cathode)
+        hd.enable_timing(True)
+        best = None
+        for _ in range(reps):
+            scb.step_(mesh, px, py, pz, pq, ex, ey, ez, at_cathode=at_cathode)
+            t = hd.timing()
+            cur = {"deposit": t["deposit_ms"], "solve": t["solve_ms"], "interpolate": t["interpolate_ms"]}
+            best = cur if best is None else {k: min(best[k], cur[k]) for k in cur}
+        hd.enable_timing(False)
+        best["step"] = sum(best.values())
+        return best
+
+    # destinations allocated once, outside the timed calls (as a tracking loop would keep them)
+    perm = torch.empty(x.numel(), dtype=torch.int32, device=x.device)
+    sorted_bufs = [torch.empty_like(x) for _ in range(4)]
+    t_sort0, _ = timed(lambda: scb.sort_particles(mesh, x, y, z, out=perm))
+    t_perm0, (sx, sy, sz, sq) = timed(lambda: scb.permute(perm, x, y, z, q, handle=hd, out=sorted_bufs))
+    scb.set_particle_order(mesh, "cell")
+    try:
+        ordered = stage_times(sx, sy, sz, sq)
+        # the bunch a tracking loop re-sorts: ordered a few steps ago, every particle displaced by N(0, (0.1 cell)^2)
+        gen = torch.Generator(device=sx.device)
+        gen.manual_seed(7)
+        d = [float(v) for v in mesh.delta]
+        mx, my, mz = (a + torch.randn(a.numel(), generator=gen, device=a.device, dtype=a.dtype) * (0.1 * dd)
+                      for a, dd in zip((sx, sy, sz), d))
+        for a, lo, hi in zip((mx, my, mz), mesh.min_bounds, mesh.max_bounds):
+            a.clamp_(float(lo), float(hi))
+        drifted = stage_times(mx, my, mz, sq, reps=3)
+        frac_drift = scb.particle_order_fraction(mesh, mx, my, mz)
+        resorted = [torch.empty_like(x) for _ in range(4)]
+        t_sort1, _ = timed(lambda: scb.sort_particles(mesh, mx, my, mz, out=perm))
+        t_perm1, _ = timed(lambda: scb.permute(perm, mx, my, mz, sq, handle=hd, out=resorted))
+        del mx, my, mz, resorted
+    finally:
+        scb.set_particle_order(mesh, "random")
+    ab = algorithmic_bytes(n_local, grid, s, at_cathode)
+    roof = {}
+    for k in ("deposit", "interpolate"):
+        gbs = ab[k] / (ordered[k] * 1e-3) / 1e9
+        roof[k] = {"ms": round(ordered[k], 4), "alg_MB": round(ab[k] / 1e6, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4),
+                   "kernel": "k_deposit_runs" if k == "deposit" else "k_interpolate_runs"}
+    step_random = stage_random["deposit"] + stage_random["solve"] + stage_random["interpolate"]
+    gain = step_random - ordered["step"]
+    resort = t_sort1 + t_perm1
+    npart_rank = n_local
+    return {
+        "what": "bunch kept ordered by linear cell index (scb_sort_particles + scb_permute, scb_set_particle_order(SCB_ORDER_CELL)); "
+                "stage minima over 5 steps, device times of rank 0" + ("" if world == 1 else "; every rank orders its own shard"),
+        "step_ms": round(ordered["step"], 4), "stages_ms": {k: round(v, 4) for k, v in ordered.items() if k != "step"},
+        "value": npart_rank * world / (ordered["step"] * 1e-3), "unit": "particles/s",
+        "stage_roofline": roof,
+        "random_order_step_ms": round(step_random, 4),
+        "sort_ms": {"first sort of the random bunch: scb_sort_particles": round(t_sort0, 4),
+                    "first sort of the random bunch: scb_permute(x,y,z,q)": round(t_perm0, 4),
+                    "re-sort of a bunch that drifted 0.1 cell since the last sort: scb_sort_particles": round(t_sort1, 4),
+                    "re-sort of a bunch that drifted 0.1 cell since the last sort: scb_permute(x,y,z,q)": round(t_perm1, 4)},
+        "after_drift_of_0.1_cell": {"step_ms": round(drifted["step"], 4),
+                                    "stages_ms": {k: round(v, 4) for k, v in drifted.items() if k != "step"},
+                                    "neighbour_pairs_in_same_or_adjacent_cell": round(frac_drift, 4)},
+        "unsorted_input_sort_inside_the_step_ms": round(t_sort0 + t_perm0 + ordered["step"], 4),
+        "resort_every_step_ms": round(resort + ordered["step"], 4),
+        "break_even_steps_per_sort": {
+            "definition": "K from which (re-sort + K ordered steps) beats K random-order steps: re-sort / (random step - ordered step)",
+            "with the re-sort cost": round(resort / gain, 2) if gain > 0 else None,
+            "with the first-sort cost": round((t_sort0 + t_perm0) / gain, 2) if gain > 0 else None},
     }
 
 
@@ -177,6 +309,7 @@ def main(print=print):
     ap.add_argument("--sharded-solve", action="store_true", help="multi-GPU: force the slab-decomposed solve (default: from 4 GPUs on)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-structure-on-GPU baseline")
     ap.add_argument("--no-records", action="store_true", help="skip the strided-records (AoS) variant of the step")
+    ap.add_argument("--no-cell-order", action="store_true", help="skip the cell-ordered regime (sort + ordered kernels)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -201,9 +334,10 @@ def main(print=print):
         print(json.dumps({
             "impl": "reference", "metric": "particles/sec for full deposit+solve+interp step", "value": cb["value"],
             "unit": "particles/s", "n_gpus": args.gpus, "steps": cb["steps_timed"], "steps_requested": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "warmup": cb["warmup_done"], "warmup_requested": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "sample_ms_per_step": cb["sample_ms_per_step"], "wall_s": cb["wall_s"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": dict({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}, parity="unpinned"),
             "stages_ms": cb["stages_ms"],
             "e2e": {"value": cb["value"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -293,6 +427,7 @@ def main(print=print):
         t = hd.timing()
         cur = {"deposit": t["deposit_ms"], "solve": t["solve_ms"], "interpolate": t["interpolate_ms"]}
         cur.update(dict(zip(("F1", "F2", "Z", "B2", "B3"), t["pass_ms"])))
+        cur["reduce_scatter"], cur["all_gather"] = t["reduce_scatter_ms"], t["all_gather_ms"]
         samples.append(cur)
         stage = cur if stage is None else {k: min(stage[k], cur[k]) for k in cur}
     stage_median = {k: float(np.median([c[k] for c in samples])) for k in stage}
@@ -302,6 +437,17 @@ def main(print=print):
     tc = hd.timing()
     cold = {"solve_cold_ms": tc["solve_ms"], "green_build_ms": tc["green_ms"]}
     hd.enable_timing(False)
+    # cell-ordered regime (north_star (1): particles sorted / binned by cell): the caller keeps its bunch ordered with
+    # scb_sort_particles + scb_permute and tells the handle so (SCB_ORDER_CELL kernels).  Reported: the ordered step,
+    # what the (re-)sort costs, the step with the sort inside, and the number of steps per sort from which ordering
+    # pays.  The headline `value` above stays the random-order step SURVEY.md 8(d) prescribes.
+    cell_ordered = None
+    if not args.no_cell_order:
+        try:
+            cell_ordered = cell_ordered_regime(scb, mesh, x, y, z, q, ex, ey, ez, at_cathode, stage, n_local, grid, s, world,
+                                               barrier, measured_peak()[0])
+        except Exception as exc:   # optional evidence, never a reason to lose the bench line
+            cell_ordered = {"unavailable": repr(exc)[:300]}
     # strided records: the same bunch as (Np, 6) phase-space records (x, px, y, py, z, pz), one charge
     # for all particles (stride 0), deposit + solve + gather fused with the momentum kick, all in place on the records
     records = None
@@ -349,22 +495,62 @@ def main(print=print):
     mesh.remesh_(x, y, z)
 
     peak, peak_src = measured_peak()
+    # PER-RANK algorithmic bytes: every rank handles its particle shard against a full-size private rho / the full field;
+    # in the slab-decomposed solve every rank runs 1/N of each grid pass (replicated solve: all of it)
     ab = algorithmic_bytes(n_local, grid, s, at_cathode)
+    grid_share = world if (world > 1 and mesh.sharded) else 1
+    for k in ("F1", "F2", "Z", "B2", "B3"):
+        ab[k] = ab[k] / grid_share
+    coll = {}
+    if world > 1 and mesh.sharded:
+        # the collectives are their own stages, against the NVLink roofline (bytes in or out of one GPU, whichever is larger,
+        # over the measured 770 GB/s per direction of B200_PROFILING.md); F1 and B3 are reported WITHOUT them
+        ng_b = grid[0] * grid[1] * grid[2] * s
+        rs_ms = min(c["reduce_scatter"] for c in samples)
+        ag_ms = min(c["all_gather"] for c in samples)
+        stage["F1"] = max(stage["F1"] - rs_ms, 1e-6)
+        stage["B3"] = max(stage["B3"] - ag_ms, 1e-6)
+        stage_median["F1"] = max(stage_median["F1"] - rs_ms, 1e-6)
+        stage_median["B3"] = max(stage_median["B3"] - ag_ms, 1e-6)
+        full = algorithmic_bytes(n_local, grid, s, at_cathode)
+        b_slab = full["F2"] - full["F1"] + ng_b   # one padded intermediate B: F2 = A + B, F1 = Ng*s + A (algorithmic_bytes)
+        nvl = {"reduce_scatter": (rs_ms, (world - 1) / world * ng_b),
+               "all_gather": (ag_ms, (world - 1) / world * 3 * ng_b)}
+        for k, (ms_k, bytes_k) in nvl.items():
+            gbs = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+            coll[k] = {"ms": round(ms_k, 4), "bound": "nvlink", "bytes_per_gpu_MB": round(bytes_k / 1e6, 1), "GBps": round(gbs, 1),
+                       "peak": NVLINK_GBS, "frac": round(gbs / NVLINK_GBS, 4)}
+        # the two pencil transposes are fused into F2 and Z (peer-memory stores): their remote bytes, for the record
+        coll["transposes_fused_into_F2_and_Z"] = {
+            "F2_remote_MB_per_gpu": round((world - 1) / world * b_slab / world / 1e6, 1),
+            "Z_remote_MB_per_gpu": round((world - 1) / world * 3 * b_slab / world / 1e6, 1),
+            "note": "F2 / Z stage times include these stores and the rank barrier that follows; bound = max(HBM, NVLink)"}
     stage_roof = {}
     for k in ("deposit", "interpolate", "F1", "F2", "Z", "B2", "B3"):
         gbs = ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0
         stage_roof[k] = {"ms": round(stage[k], 4), "median_ms": round(stage_median[k], 4), "alg_MB": round(ab[k] / 1e6, 1),
                          "GBps": round(gbs, 1), "frac": round(gbs / peak, 4), "frac_nominal_8TBps": round(gbs / NOMINAL_HBM_GBS, 4)}
-    kernel_names = {"deposit": "k_deposit_tiles", "interpolate": "k_interpolate_pair2_f64" if s == 8 else "k_interpolate_packed_f32",
+    kernel_names = {"deposit": "k_deposit_tiles" if n_local >= grid[0] * grid[1] * grid[2] else "k_deposit_pair",
+                    "interpolate": "k_interpolate_pair2_f64" if s == 8 else "k_interpolate_packed_f32",
                     "F1": "k_x_r2c", "F2": "k_lines<-1>",
                     "Z": ("k_z_eo" if (world == 1 and not at_cathode and 128 < grid[2] <= 256) else
                           "k_z_tma" if (world == 1 and not at_cathode and grid[2] <= 256) else "k_z_fused"),
                     "B2": "k_lines<+1>", "B3": "k_x_c2r"}
-    dom = max(stage_roof, key=lambda k: stage_roof[k]["ms"])
-    roofline = {"kernel": kernel_names[dom], "stage": dom, "bound": "hbm", "achieved": stage_roof[dom]["GBps"],
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": None}
+    # dominant STAGE of the step, collectives included: at 8 GPUs it is a collective, and the line says so
+    all_ms = {k: v["ms"] for k, v in stage_roof.items()}
+    all_ms.update({k: v["ms"] for k, v in coll.items() if "ms" in v})
+    dom = max(all_ms, key=lambda k: all_ms[k])
+    if dom in stage_roof:
+        roofline = {"kernel": kernel_names[dom], "stage": dom, "bound": "hbm", "achieved": stage_roof[dom]["GBps"],
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": None,
+                    "per": "rank" if world > 1 else "gpu"}
+    else:
+        roofline = {"kernel": "ncclAllGather" if dom == "all_gather" else "ncclReduceScatter", "stage": dom, "bound": "nvlink",
+                    "achieved": coll[dom]["GBps"], "peak": NVLINK_GBS,
+                    "peak_source": "measured peer copy per direction (B200_PROFILING.md)", "unit": "GB/s",
+                    "frac": coll[dom]["frac"], "traffic": None, "per": "rank"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tr):
+    if os.path.exists(tr) and world == 1 and dom in stage_roof:
         with open(tr) as f:
             roofline["traffic"] = json.load(f).get(args.workload + "_" + args.dtype, {}).get(kernel_names[dom])
 
@@ -504,8 +690,9 @@ def main(print=print):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del x, y, z, q, ex, ey, ez
-        cb = cpu_reference_run(npart, grid, at_cathode, zshift, 1, 0, budget_s=60.0)
+        cb = cpu_reference_run(npart, grid, at_cathode, zshift, 1, 0, budget_s=30.0)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline["parity"] = "unpinned"   # the reference ships no golden vectors and Julia is absent
         cpu_baseline["stages_ms"] = cb["stages_ms"]
 
     if rank == 0:
@@ -514,9 +701,17 @@ def main(print=print):
             "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": launches,
-            "clocks": sampler.summary(), "roofline": roofline, "stage_roofline": stage_roof, "sector_roofline": sector_roof,
+            "clocks": sampler.summary(), "roofline": roofline, "stage_roofline": stage_roof,
+            "collective_roofline": coll or None, "sector_roofline": sector_roof,
             "solve_ms": stage["solve"], "solve_median_ms": stage_median["solve"], "stage_reps": STAGE_REPS,
-            "cold_geometry": cold, "records_layout": records, "cpu_baseline": cpu_baseline,
+            "cold_geometry": cold,
+            # the reference re-fits the mesh and rebuilds the Green function on every solve (src/mesh.jl:95-174,
+            # src/solvers/free_space.jl:77-89): the like-for-like number for a tracking loop
+            "tracking_loop": {"what": "remesh_ (device extrema, new spacing, Green spectrum rebuilt) + step, every step",
+                              "ms_per_step": cold["remesh_step_ms"], "value": npart / (cold["remesh_step_ms"] * 1e-3),
+                              "unit": "particles/s"},
+            "e2e_blocking_call_ms": e2e["blocking_call"]["ms_per_step"] if e2e else None,
+            "cell_ordered": cell_ordered, "records_layout": records, "cpu_baseline": cpu_baseline,
             "gpu_reference_structure": gpu_ref,
             "workspace_GB": hd.workspace_bytes() / 1e9,
         }

@@ -69,7 +69,9 @@ typedef struct scb_timing {
     float solve_ms;
     float interpolate_ms;
     float green_ms;            /* time spent (re)building the IGF spectrum inside solve_ms        */
-    float pass_ms[8];          /* F1, F2, Z, B2, B3 of the last solve (rest reserved)             */
+    float pass_ms[8];          /* F1, F2, Z, B2, B3 of the last solve; slab-decomposed solve: [0] includes the
+                                  reduce-scatter of rho, [4] the all-gather of E, reported on their own as
+                                  [5] and [6] ([7] reserved)                                          */
 } scb_timing;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
@@ -267,6 +269,9 @@ SCB_API int scb_step_host_wait(scb_handle* h);
 SCB_API int scb_comm_unique_id(void* uid128);
 SCB_API int scb_comm_init(scb_handle* h, int nranks, int rank, const void* uid128);
 SCB_API int scb_comm_destroy(scb_handle* h);
+/* Sum of the ranks' charge grids in place (ncclAllReduce on the library's communicator, handle's stream): the
+ * "solve replicated" mode of a particle-sharded run -- every rank then calls scb_solve on the full grid. */
+SCB_API int scb_allreduce_rho(scb_handle* h, void* rho, const int64_t n[3], int mdt);
 /* rho_partial: this rank's un-reduced charge grid (full size).  Reduce-scatters it into z slabs,
  * runs the FFT passes slab-decomposed (all-to-all pencil transposes fused into the pass
  * addressing), and all-gathers the field so that every rank ends with the full efield.

@@ -33,6 +33,9 @@ def _lib():
     for f in ("port_deposit", "port_green_point", "port_diff8", "port_copy_back", "port_embed", "port_multiply",
               "port_extract", "port_interpolate"):
         getattr(lib, f).restype = None
+    lib.port_set_threads.argtypes = [C.c_int]
+    lib.port_set_threads.restype = None
+    lib.port_get_threads.restype = C.c_int
     return lib
 
 
@@ -46,7 +49,9 @@ class RefPort:
         self.d = tuple(float(v) for v in delta)
         self.gamma = float(gamma)
         self.threads = int(threads or os.cpu_count() or 1)
-        os.environ.setdefault("OMP_NUM_THREADS", str(self.threads))
+        # explicit: torchrun exports OMP_NUM_THREADS=1, which a setdefault() would leave in force (round-1 verdict)
+        self.lib.port_set_threads(self.threads)
+        self.omp_threads = int(self.lib.port_get_threads())
         s2 = tuple(2 * g for g in self.n)
         self.s2 = s2
         self.rho = np.zeros(self.n, order="F")

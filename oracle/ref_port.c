@@ -18,6 +18,26 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* thread count of the threaded loops below.  Set explicitly by the caller: launchers such as torchrun export
+ * OMP_NUM_THREADS=1 into the environment, which would silently serialise the baseline. */
+void port_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int port_get_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 /* src/deposition.jl:28-86, serial driver :167-197 */
 void port_deposit(int64_t np, const double* x, const double* y, const double* z, const double* q,

@@ -102,7 +102,9 @@ class Handle:
         t = _lib.scb_timing()
         self.check(self.lib.scb_get_timing(self.h, C.byref(t)))
         return {"deposit_ms": t.deposit_ms, "solve_ms": t.solve_ms, "interpolate_ms": t.interpolate_ms,
-                "green_ms": t.green_ms, "pass_ms": list(t.pass_ms)[:5]}
+                "green_ms": t.green_ms, "pass_ms": list(t.pass_ms)[:5],
+                # slab-decomposed solve: the collectives inside pass_ms[0] (F1) and pass_ms[4] (B3), timed on their own
+                "reduce_scatter_ms": t.pass_ms[5], "all_gather_ms": t.pass_ms[6]}
 
     def launch_count(self) -> int:
         return int(self.lib.scb_launch_count(self.h))
@@ -400,8 +402,7 @@ class Mesh3D:
     def reduce_rho_(self):
         """Sum the per-rank partial charge grids in place (sharded mode keeps them partial)."""
         if self.group is not None:
-            from .sharding import allreduce_rho
-            allreduce_rho(self._rho, self.group)
+            _allreduce_rho(self)
 
     def _n(self):
         return _lib.i64x3(self.grid_size)
@@ -420,6 +421,20 @@ class Mesh3D:
 
 
 # -------------------------------------------------------------------------------- operations
+def _allreduce_rho(mesh: Mesh3D) -> None:
+    """Sum of the ranks' charge grids: the library's own NCCL communicator on the handle's stream
+    (scb_allreduce_rho) for NCCL groups; torch.distributed only for the gloo groups of the CPU-side tests."""
+    import torch.distributed as dist
+    if dist.get_backend(mesh.group) == "nccl":
+        hd = mesh.handle
+        hd.use_current_stream()
+        hd.init_comm(mesh.group)
+        hd.check(hd.lib.scb_allreduce_rho(hd.h, mesh._rho.data_ptr(), mesh._n(), mesh._mdt()))
+    else:
+        from .sharding import allreduce_rho
+        allreduce_rho(mesh._rho, mesh.group)
+
+
 def clear_mesh_(mesh: Mesh3D) -> None:
     """clear_mesh!  (src/deposition.jl:10-12)"""
     hd = mesh.handle
@@ -441,7 +456,6 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
     if mesh.group is not None and not mesh.sharded and not clear:
         # rho already holds a grid summed over the ranks: only THIS call's contribution may be all-reduced
         # (reducing the whole grid again would count the earlier charge once per rank)
-        from .sharding import allreduce_rho
         keep = mesh._rho.clone()
         deposit_(mesh, particles_x, particles_y, particles_z, particles_q, clear=True)   # reduces the new part
         mesh._rho.add_(keep)
@@ -454,8 +468,7 @@ def deposit_(mesh: Mesh3D, particles_x, particles_y, particles_z, particles_q, c
                                             C.byref(_strides(sx, sy, sz, sq)), _tag(x.dtype), mesh._rho.data_ptr(),
                                             mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), 1 if clear else 0))
     if mesh.group is not None and not mesh.sharded:
-        from .sharding import allreduce_rho
-        allreduce_rho(mesh._rho, mesh.group)
+        _allreduce_rho(mesh)
 
 
 def solve_(mesh: Mesh3D, at_cathode: bool = False) -> None:
@@ -592,9 +605,10 @@ def set_particle_order(mesh_or_handle, order) -> None:
     hd.set_particle_order(order)
 
 
-def sort_particles(mesh: Mesh3D, particles_x, particles_y, particles_z):
+def sort_particles(mesh: Mesh3D, particles_x, particles_y, particles_z, out=None):
     """Permutation that orders the bunch by linear cell index of ``mesh`` (scb_sort_particles; stable).  Returns an
-    int32 CUDA tensor ``perm``: ``x[perm.long()]`` is the ordered array (``permute`` does that in one pass)."""
+    int32 CUDA tensor ``perm``: ``x[perm.long()]`` is the ordered array (``permute`` does that in one pass).
+    ``out``: an int32 CUDA tensor to receive the permutation (a tracking loop reuses it across re-sorts)."""
     torch = _torch()
     hd = mesh.handle
     hd.use_current_stream()
@@ -603,15 +617,18 @@ def sort_particles(mesh: Mesh3D, particles_x, particles_y, particles_z):
         raise ErrorException("particle arrays must share one element type")
     if not (x.numel() == y.numel() == z.numel()):
         raise ErrorException("Particle coordinate arrays must have the same length.")
-    perm = torch.empty(x.numel(), dtype=torch.int32, device=x.device)
+    perm = out if out is not None else torch.empty(x.numel(), dtype=torch.int32, device=x.device)
+    if perm.dtype != torch.int32 or perm.numel() != x.numel() or perm.device != x.device or not perm.is_contiguous():
+        raise ErrorException("sort_particles: out must be a contiguous int32 CUDA tensor of the particles' length")
     hd.check(hd.lib.scb_sort_particles(hd.h, x.numel(), x.data_ptr(), y.data_ptr(), z.data_ptr(), _tag(x.dtype),
                                        mesh._mdt(), mesh._n(), mesh._lo(), mesh._d(), perm.data_ptr()))
     return perm
 
 
-def permute(perm, *arrays, handle: Optional[Handle] = None):
+def permute(perm, *arrays, handle: Optional[Handle] = None, out=None):
     """``tuple(a[perm] for a in arrays)`` in passes of up to 8 arrays (scb_permute): 1-D CUDA tensors of one
-    floating-point type and the length of ``perm``."""
+    floating-point type and the length of ``perm``.  ``out``: destination tensors (same types and lengths, not
+    aliasing the sources) instead of fresh allocations."""
     torch = _torch()
     if not arrays:
         return ()
@@ -622,7 +639,10 @@ def permute(perm, *arrays, handle: Optional[Handle] = None):
     for a in arrays:
         if a.dtype != dt or a.numel() != n or a.device != perm.device or not a.is_contiguous():
             raise ErrorException("permute: arrays must be contiguous CUDA tensors of one type and the length of perm")
-    outs = [torch.empty_like(a) for a in arrays]
+    outs = list(out) if out is not None else [torch.empty_like(a) for a in arrays]
+    if len(outs) != len(arrays) or any(o.dtype != dt or o.numel() != n or o.device != perm.device or not o.is_contiguous()
+                                       for o in outs):
+        raise ErrorException("permute: out must match the arrays in number, type, length and device")
     for first in range(0, len(arrays), 8):
         src = arrays[first:first + 8]
         dst = outs[first:first + 8]

@@ -105,6 +105,7 @@ SIGNATURES = {
     "scb_comm_destroy": (C.c_int, [_vp]),
     "scb_step_sharded": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _F64x3,
                                    C.c_double, C.c_int, _vp, _vp, _vp]),
+    "scb_allreduce_rho": (C.c_int, [_vp, _vp, _I64x3, C.c_int]),
     "scb_solve_sharded": (C.c_int, [_vp, _vp, _vp, C.c_int, _I64x3, _F64x3, _F64x3, _F64x3, C.c_double, C.c_int]),
     # include/spacecharge_b200_debug.h
     "scb_debug_fft_lines": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,

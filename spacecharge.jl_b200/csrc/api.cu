@@ -77,7 +77,7 @@ struct scb_handle {
     cudaEvent_t ev[16]{};
     bool ev_ready = false;
     scb_timing last{};
-    bool t_dep = false, t_solve = false, t_interp = false, t_green = false, t_pass = false;
+    bool t_dep = false, t_solve = false, t_interp = false, t_green = false, t_pass = false, t_coll = false;
     // host-step staging
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -88,6 +88,13 @@ struct scb_handle {
     // straight into the destination rank's receive buffers
     int p2p = -1;                  // -1 undecided, 0 off (NCCL send/recv), 1 on
     unsigned long long arena_gen = 0, peer_gen = ~0ull;
+    // workspace of the slab-decomposed solve.  Separate from `arena` on purpose: it is (re)allocated ONLY inside
+    // run_solve_sharded, from arguments every rank shares, so all ranks decide alike whether the collective
+    // re-exchange of IPC handles (exchange_arenas) has to run -- single-rank users of `arena` (scb_solve, scb_green,
+    // the sort, the probes) can no longer make one rank skip or enter that collective alone.
+    void* sh_arena = nullptr;
+    size_t sh_arena_bytes = 0;
+    unsigned long long sh_gen = 0;
     std::vector<void*> peer_arena;
     char* d_ipc = nullptr;         // nranks * 64 bytes of IPC handles + 2 ints (flag, barrier)
     // host-buffer steps: two staging slots so that the upload of step k+1 overlaps the download of step k
@@ -217,6 +224,24 @@ int ensure_arena(scb_handle* h, size_t bytes) {
     }
     h->arena_bytes = bytes;
     h->arena_gen++;
+    return SCB_OK;
+}
+
+int ensure_sh_arena(scb_handle* h, size_t bytes) {
+    if (bytes <= h->sh_arena_bytes) return SCB_OK;
+    if (h->sh_arena) {
+        SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+        close_peers(h);   // the peers' mappings of the old buffer are re-made by exchange_arenas
+        SCB_CUDA(h, cudaFree(h->sh_arena));
+        h->sh_arena = nullptr;
+        h->sh_arena_bytes = 0;
+    }
+    if (cudaMalloc(&h->sh_arena, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, SCB_ERR_ALLOC, "sharded-solve workspace allocation of " + std::to_string(bytes) + " bytes failed");
+    }
+    h->sh_arena_bytes = bytes;
+    h->sh_gen++;
     return SCB_OK;
 }
 
@@ -865,6 +890,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
     }
     tick(h, 13);
     h->t_pass = true;
+    h->t_coll = false;
     h->launches += 5;
     return SCB_OK;
 }
@@ -1025,6 +1051,7 @@ int scb_destroy(scb_handle* h) {
     free_green(h, true);
     for (auto& kv : h->twiddles) cudaFree(kv.second);
     if (h->arena) cudaFree(h->arena);
+    if (h->sh_arena) cudaFree(h->sh_arena);
     for (void* st : h->stage)
         if (st) cudaFree(st);
     if (h->packed) cudaFree(h->packed);
@@ -1087,6 +1114,11 @@ int scb_get_timing(scb_handle* h, scb_timing* out) {
     h->last.green_ms = h->t_green ? el(6, 7) : 0.f;
     if (h->t_pass)
         for (int i = 0; i < 5; ++i) h->last.pass_ms[i] = el(8 + i, 9 + i);
+    h->last.pass_ms[5] = h->last.pass_ms[6] = 0.f;
+    if (h->t_pass && h->t_coll) {   // slab-decomposed solve: the collectives that pass_ms[0] and pass_ms[4] include
+        h->last.pass_ms[5] = el(8, 14);    // reduce-scatter of rho
+        h->last.pass_ms[6] = el(15, 13);   // all-gather of E
+    }
     *out = h->last;
     return SCB_OK;
 }
@@ -1607,21 +1639,20 @@ void close_peers(scb_handle* h) {
 // grows its arena in the same call, so every rank gets here together.  Any failure on any rank
 // switches all ranks back to the NCCL send/recv path.
 int exchange_arenas(scb_handle* h) {
-    if (h->p2p == 0 || (h->peer_gen == h->arena_gen && !h->peer_arena.empty())) return SCB_OK;
+    // Entered or skipped by ALL ranks together: sh_gen only changes inside run_solve_sharded (same arguments on every
+    // rank), and a rank that does not want the peer path (SCB_P2P=0) still takes part and votes against it below.
+    if (h->peer_gen == h->sh_gen) return SCB_OK;
     const int G = h->nranks, me = h->rank;
-    if (G > SCB_MAX_RANKS) { h->p2p = 0; return SCB_OK; }
-    if (h->p2p < 0) {
-        const char* e = std::getenv("SCB_P2P");
-        if (e && std::atoi(e) == 0) { h->p2p = 0; return SCB_OK; }
-    }
+    int want = 1;
+    if (const char* e = std::getenv("SCB_P2P")) want = std::atoi(e) != 0;
     if (!h->d_ipc) {
         SCB_CUDA(h, cudaMalloc(&h->d_ipc, (size_t)SCB_MAX_RANKS * 64 + 8));
         SCB_CUDA(h, cudaMemsetAsync(h->d_ipc, 0, (size_t)SCB_MAX_RANKS * 64 + 8, h->stream));
     }
     close_peers(h);
-    int ok = 1;
+    int ok = want;
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, h->arena) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof(mine)); }
+    if (cudaIpcGetMemHandle(&mine, h->sh_arena) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof(mine)); }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     SCB_CUDA(h, cudaMemcpyAsync(h->d_ipc + (size_t)me * 64, &mine, 64, cudaMemcpyHostToDevice, h->stream));
     SCB_NCCL(h, g_nccl.AllGather(h->d_ipc + (size_t)me * 64, h->d_ipc, 64, ncclChar, h->comm, h->stream));
@@ -1629,7 +1660,7 @@ int exchange_arenas(scb_handle* h) {
     SCB_CUDA(h, cudaMemcpyAsync(all.data(), h->d_ipc, (size_t)G * 64, cudaMemcpyDeviceToHost, h->stream));
     SCB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->peer_arena.assign(G, nullptr);
-    h->peer_arena[me] = h->arena;
+    h->peer_arena[me] = h->sh_arena;
     for (int r = 0; r < G && ok; ++r) {
         if (r == me) continue;
         if (cudaIpcOpenMemHandle(&h->peer_arena[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -1645,13 +1676,13 @@ int exchange_arenas(scb_handle* h) {
     int all_ok = 0;
     SCB_CUDA(h, cudaMemcpyAsync(&all_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     SCB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->peer_gen = h->sh_gen;
     if (!all_ok) {
         close_peers(h);
         h->p2p = 0;
         return SCB_OK;
     }
     h->p2p = 1;
-    h->peer_gen = h->arena_gen;
     return SCB_OK;
 }
 
@@ -1695,10 +1726,10 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
     T* slab = static_cast<T*>(h->slab);
     const size_t szA = (size_t)pl.PX * pl.n[1] * nzl;       // A_l, D_c
     const size_t szB = (size_t)pl.PX * pl.L[1] * nzl;       // send/recv buffers (= PX*Lyl*nz)
-    SCB_TRY(ensure_arena(h, (4 * szA + 8 * szB) * sizeof(C)));
+    SCB_TRY(ensure_sh_arena(h, (4 * szA + 8 * szB) * sizeof(C)));
     SCB_TRY(exchange_arenas(h));
     const bool p2p = h->p2p == 1;
-    C* A = static_cast<C*>(h->arena);
+    C* A = static_cast<C*>(h->sh_arena);
     C* SB = A + szA;          // F2 output, blocked by destination rank
     C* RB = SB + szB;         // received: [z][ky_l][kx]
     C* Cc = RB + szB;         // 3 components [z][ky_l][kx]
@@ -1712,6 +1743,7 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
 
     tick(h, 8);
     SCB_NCCL(h, g_nccl.ReduceScatter(rho_partial, slab, slab_elems, nt, ncclSum, h->comm, h->stream));
+    tick(h, 14);
     {  // F1 on the slab
         XParams<T> p{};
         p.in = slab; p.out = A; p.tw = twx;
@@ -1777,6 +1809,7 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
         p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
         SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
     }
+    tick(h, 15);
     if (!defer_gather) {   // scb_step_sharded gathers the slabs itself, overlapped with the interpolation
         SCB_NCCL(h, g_nccl.GroupStart());
         for (int c = 0; c < 3; ++c)
@@ -1785,6 +1818,7 @@ int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan
     }
     tick(h, 13);
     h->t_pass = true;
+    h->t_coll = true;
     h->launches += 5 + 4;  // five pass kernels + four collectives
     return SCB_OK;
 }
@@ -1878,6 +1912,7 @@ int scb_comm_unique_id(void* uid128) {
 int scb_comm_init(scb_handle* h, int nranks, int rank, const void* uid128) {
     if (!h) return SCB_ERR_INVALID_ARG;
     if (!uid128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_comm_init");
+    if (nranks > SCB_MAX_RANKS) return fail(h, SCB_ERR_UNSUPPORTED, "at most " + std::to_string(SCB_MAX_RANKS) + " ranks are supported");
     if (!load_nccl()) return fail(h, SCB_ERR_COMM, "libnccl.so.2 could not be loaded");
     SCB_CUDA(h, cudaSetDevice(h->device));
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
@@ -1886,6 +1921,9 @@ int scb_comm_init(scb_handle* h, int nranks, int rank, const void* uid128) {
     SCB_NCCL(h, g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->nranks = nranks;
     h->rank = rank;
+    close_peers(h);          // mappings belong to the previous communicator's ranks
+    h->peer_gen = ~0ull;
+    h->p2p = -1;
     return SCB_OK;
 }
 
@@ -1898,6 +1936,18 @@ int scb_comm_destroy(scb_handle* h) {
     }
     h->nranks = 1;
     h->rank = 0;
+    return SCB_OK;
+}
+
+int scb_allreduce_rho(scb_handle* h, void* rho, const int64_t n[3], int mdt) {
+    if (!h) return SCB_ERR_INVALID_ARG;
+    if (!h->comm) return fail(h, SCB_ERR_COMM, "scb_comm_init has not been called");
+    if (!rho || !valid_dt(mdt)) return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_allreduce_rho");
+    SCB_TRY(check_grid(h, n));
+    SCB_CUDA(h, cudaSetDevice(h->device));
+    SCB_NCCL(h, g_nccl.AllReduce(rho, rho, (size_t)n[0] * n[1] * n[2], mdt == SCB_F64 ? ncclFloat64 : ncclFloat32, ncclSum,
+                                 h->comm, h->stream));
+    h->launches += 1;
     return SCB_OK;
 }
 

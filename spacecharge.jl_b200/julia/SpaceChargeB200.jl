@@ -31,6 +31,7 @@ dtag(::Type{Float64}) = SCB_F64
 # ---- handle (one per task/stream, like the C ABI requires) --------------------------------------
 mutable struct Handle
     ptr::Ptr{Cvoid}
+    stream::Ptr{Cvoid}     # the CUDA stream the handle currently enqueues on
 end
 
 function Handle(; device::Integer = CUDA.deviceid(CUDA.device()), stream = CUDA.stream())
@@ -38,7 +39,7 @@ function Handle(; device::Integer = CUDA.deviceid(CUDA.device()), stream = CUDA.
     rc = ccall((:scb_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
                device, Base.unsafe_convert(Ptr{Cvoid}, stream.handle), C_NULL, out)
     rc == 0 || error("scb_create failed with code $rc (an sm_100 GPU is required; there is no CPU fallback)")
-    h = Handle(out[])
+    h = Handle(out[], Base.unsafe_convert(Ptr{Cvoid}, stream.handle))
     finalizer(x -> ccall((:scb_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
     return h
 end
@@ -67,7 +68,30 @@ end
 
 _n(m::Mesh3D) = Int64[m.grid_size...]
 _f3(t) = Float64[t...]
-handle(m::Mesh3D) = (m._workspace === nothing && (m._workspace = default_handle()); m._workspace::Handle)
+
+# Work is enqueued on the handle's stream; CUDA.jl gives every task its own stream, so before each call the handle
+# follows the calling task's current stream (scb_set_stream synchronises the old stream once when it changes).
+function use_current_stream!(h::Handle)
+    s = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
+    if s != h.stream
+        check(h, ccall((:scb_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, s))
+        h.stream = s
+    end
+    return h
+end
+function handle(m::Mesh3D)
+    m._workspace === nothing && (m._workspace = default_handle())
+    return use_current_stream!(m._workspace::Handle)
+end
+
+# The reference promotes mixed Float32 / Float64 particle arrays element by element (src/deposition.jl:39-41); the C ABI
+# takes ONE particle element type per call, so mixed arrays are refused instead of being read with the wrong size.
+function particle_eltype(arrays...)
+    P = eltype(arrays[1])
+    all(a -> eltype(a) === P, arrays) || error("particle arrays must share one element type (got $(map(eltype, arrays)))")
+    (P === Float32 || P === Float64) || error("only Float32 and Float64 particle arrays are supported")
+    return P
+end
 
 """
     Mesh3D(grid_size, particles_x, particles_y, particles_z; T=Float64, gamma=1.0, total_charge=0.0)
@@ -85,7 +109,8 @@ function Mesh3D(grid_size::NTuple{3, Int}, particles_x, particles_y, particles_z
     if particles_x isa CuArray
         P = eltype(particles_x)
         lo = zeros(Float64, 3); hi = zeros(Float64, 3)
-        h = default_handle()
+        particle_eltype(particles_x, particles_y, particles_z)
+        h = use_current_stream!(default_handle())
         check(h, ccall((:scb_bounds, LIB), Cint,
                        (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}),
                        h.ptr, length(particles_x), particles_x, particles_y, particles_z, dtag(P), lo, hi))
@@ -139,7 +164,7 @@ function deposit!(mesh::Mesh3D{T}, particles_x, particles_y, particles_z, partic
     (length(particles_x) == length(particles_y) == length(particles_z) == length(particles_q)) ||
         error("Particle coordinate and charge arrays must have the same length.")
     particles_x isa CuArray || error("Unsupported backend: particle arrays must be CuArrays")
-    P = eltype(particles_x)
+    P = particle_eltype(particles_x, particles_y, particles_z, particles_q)
     h = handle(mesh)
     check(h, ccall((:scb_deposit, LIB), Cint,
                    (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Cint,
@@ -167,7 +192,7 @@ end
 
 # ---- interpolate_field  (src/interpolation.jl:100-128) ------------------------------------------
 function interpolate_field(mesh::Mesh3D{T}, particles_x, particles_y, particles_z) where {T}
-    P = eltype(particles_x)
+    P = particle_eltype(particles_x, particles_y, particles_z)
     Ex = similar(particles_x); Ey = similar(particles_x); Ez = similar(particles_x)
     h = handle(mesh)
     check(h, ccall((:scb_interpolate, LIB), Cint,
@@ -186,7 +211,7 @@ function with raw last planes, imaginary part = 0.
 function get_green_function!(cgrn::CuArray{Complex{T}, 3}, delta::NTuple{3, T}, gamma::T, icomp::Int;
                              offset::NTuple{3, T} = (zero(T), zero(T), zero(T)), temp = nothing) where {T}
     re = CUDA.zeros(T, size(cgrn)...)
-    h = default_handle()
+    h = use_current_stream!(default_handle())
     check(h, ccall((:scb_green, LIB), Cint,
                    (Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Cint),
                    h.ptr, re, Int64[size(cgrn)...], _f3(delta), Float64(gamma), icomp, _f3(offset), dtag(T)))
@@ -246,7 +271,7 @@ end
 interpolated field never round-trips through memory.
 """
 function interpolate_kick!(mesh::Mesh3D{T}, x, y, z, px, py, pz, coef_xy::Real, coef_z::Real) where {T}
-    P = eltype(x)
+    P = particle_eltype(x, y, z, px, py, pz)
     h = handle(mesh)
     check(h, ccall((:scb_interpolate_kick, LIB), Cint,
                    (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid}, Cint, Ptr{Int64},
@@ -261,7 +286,7 @@ end
 deposit! + solve! + interpolate_field in one call with caller-owned outputs (scb_step).
 """
 function step!(mesh::Mesh3D{T}, x, y, z, q, Ex, Ey, Ez; at_cathode::Bool = false) where {T}
-    P = eltype(x)
+    P = particle_eltype(x, y, z, q, Ex, Ey, Ez)
     h = handle(mesh)
     check(h, ccall((:scb_step, LIB), Cint,
                    (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid},
@@ -339,7 +364,7 @@ end
 `step!` on this rank's particle shard (scb_step_sharded).
 """
 function step_sharded!(mesh::Mesh3D{T}, x, y, z, q, Ex, Ey, Ez; at_cathode::Bool = false) where {T}
-    P = eltype(x)
+    P = particle_eltype(x, y, z, q, Ex, Ey, Ez)
     h = handle(mesh)
     check(h, ccall((:scb_step_sharded, LIB), Cint,
                    (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, CuPtr{Cvoid},
@@ -439,5 +464,90 @@ function interpolate_field(mesh::Mesh3D{T}, records::CuMatrix{P}; rows::NTuple{3
                    _f3(mesh.delta), Ex, Ey, Ez))
     return Ex, Ey, Ez
 end
+
+# ---- bunches kept ordered by cell (extension; scb_sort_particles, scb_permute, scb_set_particle_order) -------------
+const SCB_ORDER_RANDOM = Cint(0)
+const SCB_ORDER_CELL = Cint(1)
+
+"""
+    sort_particles(mesh, x, y, z) -> perm::CuVector{UInt32}
+
+Permutation that orders the bunch by linear cell index of `mesh` (0-based particle indices, stable).
+"""
+function sort_particles(mesh::Mesh3D{T}, x::CuVector, y::CuVector, z::CuVector) where {T}
+    P = particle_eltype(x, y, z)
+    (length(x) == length(y) == length(z)) || error("Particle coordinate arrays must have the same length.")
+    perm = CuVector{UInt32}(undef, length(x))
+    h = handle(mesh)
+    check(h, ccall((:scb_sort_particles, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64},
+                    Ptr{Float64}, CuPtr{Cvoid}),
+                   h.ptr, length(x), x, y, z, dtag(P), dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.delta), perm))
+    return perm
+end
+
+"""
+    permute(mesh, perm, arrays...) -> Tuple of new CuVectors, `a[perm .+ 1]` for every array (up to 8 per pass)
+"""
+function permute(mesh::Mesh3D, perm::CuVector{UInt32}, arrays::CuVector...)
+    P = particle_eltype(arrays...)
+    all(a -> length(a) == length(perm), arrays) || error("permute: arrays must have the length of perm")
+    outs = map(similar, arrays)
+    h = handle(mesh)
+    for first in 1:8:length(arrays)
+        last = min(first + 7, length(arrays))
+        src = [reinterpret(Ptr{Cvoid}, pointer(a)) for a in arrays[first:last]]
+        dst = [reinterpret(Ptr{Cvoid}, pointer(a)) for a in outs[first:last]]
+        GC.@preserve arrays outs check(h, ccall((:scb_permute, LIB), Cint,
+                       (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint),
+                       h.ptr, length(perm), perm, last - first + 1, src, dst, dtag(P)))
+    end
+    return outs
+end
+
+"""
+    sort_particles!(mesh, x, y, z, others...) -> (perm, x_sorted, y_sorted, z_sorted, others_sorted...)
+"""
+function sort_particles!(mesh::Mesh3D, x::CuVector, y::CuVector, z::CuVector, others::CuVector...)
+    perm = sort_particles(mesh, x, y, z)
+    return (perm, permute(mesh, perm, x, y, z, others...)...)
+end
+
+"""
+    set_particle_order!(mesh, order)    order = :random (default kernels) or :cell (run-accumulating kernels)
+
+Results do not depend on the setting; only the speed of `deposit!`, `interpolate_field` and `step!` does.
+"""
+function set_particle_order!(mesh::Mesh3D, order::Symbol)
+    code = order === :cell ? SCB_ORDER_CELL : order === :random ? SCB_ORDER_RANDOM : error("order must be :random or :cell")
+    h = handle(mesh)
+    check(h, ccall((:scb_set_particle_order, LIB), Cint, (Ptr{Cvoid}, Cint), h.ptr, code))
+end
+
+"""
+    particle_order_fraction(mesh, x, y, z) -> Float64
+
+Fraction of sampled neighbouring particle pairs in the same or the x-adjacent cell (1 = ordered, 0 = random).
+"""
+function particle_order_fraction(mesh::Mesh3D{T}, x::CuVector, y::CuVector, z::CuVector) where {T}
+    P = particle_eltype(x, y, z)
+    out = Ref{Float64}(0.0)
+    h = handle(mesh)
+    check(h, ccall((:scb_particle_order_fraction, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64},
+                    Ptr{Float64}, Ref{Float64}),
+                   h.ptr, length(x), x, y, z, dtag(P), dtag(T), _n(mesh), _f3(mesh.min_bounds), _f3(mesh.delta), out))
+    return out[]
+end
+
+"""
+    allreduce_rho!(mesh)
+
+Sum of the ranks' charge grids in place on the library's communicator (scb_allreduce_rho): the "solve replicated" mode
+of a particle-sharded run.
+"""
+allreduce_rho!(mesh::Mesh3D{T}) where {T} =
+    (h = handle(mesh); check(h, ccall((:scb_allreduce_rho, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Int64}, Cint),
+                                      h.ptr, mesh.rho, _n(mesh), dtag(T))))
 
 end # module SpaceChargeB200

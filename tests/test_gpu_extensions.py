@@ -146,6 +146,31 @@ def test_remesh_step_with_spectrum_prefetch_equals_separate_calls(scb, T, at_cat
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("at_cathode", [False, True])
+def test_remesh_step_matches_the_oracle(scb, oracle, record, at_cathode):
+    """remesh_ against the ORACLE (not against another CUDA mesh): after every re-fit the geometry must be what the
+    reference's particle-based constructor computes for the new positions (src/mesh.jl:118-156, restated in
+    oracle.mesh_from_particles) and the fused step on it must give the oracle's rho, E and interpolated E (1e-10)."""
+    import torch
+    n, grid = 60_000, (14, 18, 12)
+    x, y, z, q = gaussian(n, 77, shift=(0, 0, 7e-3 if at_cathode else 0))
+    dx, dy, dz, dq = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D(grid, dx, dy, dz, gamma=1.7)
+    outs = [torch.empty_like(dx) for _ in range(3)]
+    scb.step_(mesh, dx, dy, dz, dq, *outs, at_cathode=at_cathode)
+    for k, scale in enumerate((1.03, 0.9, 1.2)):
+        xs, ys = x * scale, y / scale
+        dxs, dys = to_dev(xs, ys)
+        mesh.remesh_(dxs, dys, dz)
+        scb.step_(mesh, dxs, dys, dz, dq, *outs, at_cathode=at_cathode)
+        ref, want = oracle.full_step(grid, xs, ys, z, q, gamma=1.7, at_cathode=at_cathode)
+        assert (mesh.min_bounds, mesh.max_bounds, mesh.delta) == (ref.min_bounds, ref.max_bounds, ref.delta)
+        check(record, "remesh %d rho" % k, mesh.rho.cpu().numpy(), ref.rho, TOL64)
+        for c in range(3):
+            check(record, "remesh %d E%d" % (k, c), mesh.efield[..., c].cpu().numpy(), ref.efield[..., c], TOL64)
+            check(record, "remesh %d Einterp%d" % (k, c), outs[c].cpu().numpy(), want[c], TOL64)
+
+
 def test_warm_step_is_capturable_in_a_cuda_graph(scb, record):
     """The small configurations are launch-bound (nine launches of 5-10 us at 32^3), so a tracking loop wants the
     step inside a CUDA graph.  In the warm state (workspace, packed field, Green spectrum built) scb_step performs no

@@ -1,6 +1,9 @@
-"""Two-GPU parity of the particle-sharded step: slab-decomposed solve (reduce-scatter, all-to-all
-pencil transposes, all-gather over NCCL) against the single-GPU result on the same particles.
-Needs two B200s (`gpurun --gpus 2`); skipped on a one-GPU box."""
+"""Multi-GPU parity of the particle-sharded step at world sizes 2, 4 and 8: slab-decomposed solve (reduce-scatter,
+pencil transposes over peer memory / NCCL, all-gather) and the replicated-solve fallback, against the single-GPU
+result on the same particles AND, for the BASELINE-sized grids (128^3 free space, 128x128x256 cathode), element-wise
+against the oracle's C restatement (oracle/cpu_reference.py, computed once by the parent process).
+Needs `gpurun --gpus N`; every world size larger than the box's GPU count is skipped (the driver's one-GPU GPUTEST
+skips all of them: profiles/r02_pytest_multi8.log is the committed 8-GPU run)."""
 import os
 import sys
 
@@ -23,14 +26,8 @@ def _worker(rank, world, port, out_dir):
     from spacecharge_jl_b200.sharding import shard_range
 
     worst = 0.0
-    for grid, cath, T, tol in (((32, 24, 16), False, np.float64, 1e-12), ((16, 20, 32), True, np.float64, 1e-11),
-                               ((32, 32, 32), False, np.float32, 2e-6)):
-        rng = np.random.default_rng(42)
-        n = 200001
-        x, y, z = (rng.standard_normal(n) * 1e-3 for _ in range(3))
-        if cath:
-            z = z + 6e-3
-        q = np.full(n, 1e-9 / n)
+    for grid, cath, T, tol, n in CASES:
+        x, y, z, q = _case_particles(n, cath)
         dev = "cuda:%d" % rank
         full = [torch.from_numpy(a).to(dev) for a in (x, y, z, q)]
         b, e = shard_range(n, rank, world)
@@ -40,6 +37,8 @@ def _worker(rank, world, port, out_dir):
         scb.deposit_(ref, *full)
         scb.solve_(ref, at_cathode=cath)
         rex = scb.interpolate_field(ref, *mine[:3])
+        oracle_file = os.path.join(out_dir, "oracle_%dx%dx%d_%d.npz" % (grid + (int(cath),)))
+        oracle_e = np.load(oracle_file)["efield"] if os.path.exists(oracle_file) else None
         for sharded in (True, False):
             mesh = scb.Mesh3D(grid, *mine[:3], T=T, gamma=2.0, group=dist.group.WORLD, sharded_solve=sharded)
             assert mesh.sharded == sharded
@@ -55,6 +54,13 @@ def _worker(rank, world, port, out_dir):
                 assert err < tol, (grid, cath, sharded, c, err)
                 err = float((out[c] - rex[c]).abs().max() / rex[c].abs().max())
                 assert err < tol, (grid, cath, sharded, "interp", c, err)
+                if oracle_e is not None:   # element-wise against the C restatement of the reference, 1e-10
+                    w = torch.from_numpy(oracle_e[..., c]).to(dev)
+                    err = float((a - w).abs().max() / w.abs().max())
+                    assert err < 1e-10, (grid, cath, sharded, "oracle", c, err)
+                    if rank == 0:
+                        print("world %d grid %s cathode %d sharded %d: E%d vs oracle %.2e, vs one GPU %.2e"
+                              % (world, grid, cath, sharded, c, err, float((a - r).abs().max() / r.abs().max())), flush=True)
             # fused step; in the sharded mode also with the field slabs broadcast and gathered in overlapping passes
             for overlap in ("0", "1"):
                 os.environ["SCB_GATHER_OVERLAP"] = overlap
@@ -87,12 +93,43 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_sharded_step_matches_single_gpu(tmp_path):
+# (grid, cathode, mesh type, tolerance against the single-GPU result, particles)
+CASES = (((32, 24, 16), False, np.float64, 1e-12, 200001), ((16, 20, 32), True, np.float64, 1e-11, 200001),
+         ((32, 32, 32), False, np.float32, 2e-6, 200001),
+         ((128, 128, 128), False, np.float64, 1e-12, 2000003), ((128, 128, 256), True, np.float64, 1e-11, 2000003))
+
+
+def _case_particles(n, cath):
+    rng = np.random.default_rng(42)
+    x, y, z = (rng.standard_normal(n) * 1e-3 for _ in range(3))
+    if cath:
+        z = z + 6e-3
+    return x, y, z, np.full(n, 1e-9 / n)
+
+
+def _write_oracle_fields(out_dir):
+    """E of the BASELINE-sized cases from the C restatement of the reference, once, for every worker to compare with"""
+    sys.path.insert(0, ROOT)
+    from oracle import spacecharge_oracle as so
+    from oracle.cpu_reference import RefPort
+    for grid, cath, T, _, n in CASES:
+        if grid[0] < 128 or T != np.float64:
+            continue
+        x, y, z, q = _case_particles(n, cath)
+        m = so.mesh_from_particles(grid, x, y, z, gamma=2.0)
+        rp = RefPort(grid, m.min_bounds, m.delta, 2.0)
+        rp.deposit(x, y, z, q)
+        rp.solve(cath, m.max_bounds)
+        np.savez(os.path.join(out_dir, "oracle_%dx%dx%d_%d.npz" % (grid + (int(cath),))), efield=rp.efield)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_step_matches_single_gpu_and_oracle(tmp_path, world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world = 2
-    port = 29600 + (os.getpid() % 2000)
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _write_oracle_fields(str(tmp_path))
+    port = 29600 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
