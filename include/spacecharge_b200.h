@@ -225,9 +225,13 @@ SCB_API int scb_step_strided(scb_handle* h, int64_t np, const void* x, const voi
  *                     corner sums (deposit) / 24 field values (gather) in registers, warps combine their open runs
  *                     with a segmented shuffle reduction before touching memory.  Results are correct for ANY order
  *                     (a cell change merely ends a run); the speed depends on how ordered the bunch is.
+ *   SCB_ORDER_CELL_TILE  SCB_ORDER_CELL with a shared-memory tile of rho nodes under the deposit (the CTA adds finished
+ *                     runs to the tile with shared-memory atomics and flushes it with coalesced reductions).  Same
+ *                     results; measured SLOWER on B200 (shared Float64 atomics are compare-and-swap loops, and an
+ *                     ordered bunch makes a CTA's lanes collide on a handful of nodes): kept for comparison only.
  * scb_particle_order_fraction samples neighbouring particle pairs and returns the fraction that share a cell or sit in
  * x-adjacent cells (about 1 for an ordered bunch, about 0 for a random one); synchronous. */
-typedef enum scb_particle_order { SCB_ORDER_RANDOM = 0, SCB_ORDER_CELL = 1 } scb_particle_order;
+typedef enum scb_particle_order { SCB_ORDER_RANDOM = 0, SCB_ORDER_CELL = 1, SCB_ORDER_CELL_TILE = 2 } scb_particle_order;
 SCB_API int scb_sort_particles(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
                                int mdt, const int64_t n[3], const double min_bounds[3], const double delta[3],
                                uint32_t* perm_out);

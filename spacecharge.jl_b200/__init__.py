@@ -117,7 +117,7 @@ class Handle:
 
     def set_particle_order(self, order):
         """``"random"`` (default) or ``"cell"``: which kernels the particle passes use (scb_set_particle_order)."""
-        code = {"random": _lib.SCB_ORDER_RANDOM, "cell": _lib.SCB_ORDER_CELL}.get(order, order)
+        code = {"random": _lib.SCB_ORDER_RANDOM, "cell": _lib.SCB_ORDER_CELL, "cell_tile": _lib.SCB_ORDER_CELL_TILE}.get(order, order)
         self.check(self.lib.scb_set_particle_order(self.h, int(code)))
 
     def init_comm(self, group):

@@ -7,6 +7,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
 
 #include <cmath>
 #include <cstdio>
@@ -115,6 +116,9 @@ struct scb_handle {
     cudaStream_t green_stream = nullptr;
     cudaEvent_t ev_green_start = nullptr, ev_green_done = nullptr;
     bool green_pending = false;
+    // z-chunked B2 -> B3 hand-over (run_solve): B2 chunks on chunk_stream, B3 chunks on the handle's stream
+    cudaStream_t chunk_stream = nullptr;
+    cudaEvent_t ev_chunk_fork = nullptr, ev_chunk_ready[2] = {nullptr, nullptr}, ev_chunk_free[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -289,9 +293,9 @@ int ensure_packed(scb_handle* h, size_t bytes) {
 int run_deposit(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, const void* q, int pdt,
                 void* rho, int mdt, const Geom3& g, bool clear, bool cleared_already, const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
-    if (h->opt.particle_order == SCB_ORDER_CELL && !lay) {
+    if (h->opt.particle_order != SCB_ORDER_RANDOM && !lay) {
         if (clear && !cleared_already) SCB_CUDA(h, cudaMemsetAsync(rho, 0, (size_t)ng * dt_size(mdt), h->stream));
-        SCB_CUDA(h, launch_deposit_runs(pdt, mdt, np, x, y, z, q, rho, g, h->stream));
+        SCB_CUDA(h, launch_deposit_runs(pdt, mdt, np, x, y, z, q, rho, g, h->stream, h->opt.particle_order == SCB_ORDER_CELL_TILE));
         if (np > 0) h->launches += 1;
         return SCB_OK;
     }
@@ -322,7 +326,7 @@ int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
                     int mdt, const Geom3& g, void* ex, void* ey, void* ez, bool* packed_ready, const Kick& kick = Kick(),
                     const PLayout* lay = nullptr) {
     const long long ng = (long long)g.n[0] * g.n[1] * g.n[2];
-    if (h->opt.particle_order == SCB_ORDER_CELL && !lay && !(packed_ready && *packed_ready)) {
+    if (h->opt.particle_order != SCB_ORDER_RANDOM && !lay && !(packed_ready && *packed_ready)) {
         // SCB_CELL_GATHER=1 (tuning): one thread per particle straight from efield instead of the run-accumulating walk
         static const int direct = [] { const char* e = std::getenv("SCB_CELL_GATHER"); return e ? std::atoi(e) : 0; }();
         if (direct == 1) SCB_CUDA(h, launch_interpolate(pdt, mdt, np, x, y, z, efield, g, ex, ey, ez, h->stream, kick, nullptr));
@@ -347,7 +351,24 @@ int run_interpolate(scb_handle* h, int64_t np, const void* x, const void* y, con
     return SCB_OK;
 }
 
+// Stage boundaries: CUDA events for scb_get_timing (when enabled) and NVTX ranges for profilers (always; SURVEY.md
+// section 5, tracing).  Ranges nest as  scb:solve > { scb:green_build, scb:F1 ... scb:B3 }.
 void tick(scb_handle* h, int i) {
+    switch (i) {
+        case 0: nvtxRangePushA("scb:deposit"); break;
+        case 2: nvtxRangePushA("scb:solve"); break;
+        case 4: nvtxRangePushA("scb:interpolate"); break;
+        case 6: nvtxRangePushA("scb:green_build"); break;
+        case 8: nvtxRangePushA(h->nranks > 1 && h->comm ? "scb:F1 x r2c (+ reduce-scatter of rho when sharded)" : "scb:F1 x r2c"); break;
+        case 9: nvtxRangePop(); nvtxRangePushA("scb:F2 y forward (+ pencil transpose when sharded)"); break;
+        case 10: nvtxRangePop(); nvtxRangePushA("scb:Z fused z pass: fft, Green multiply, ifft x3"); break;
+        case 11: nvtxRangePop(); nvtxRangePushA("scb:B2 y inverse"); break;
+        case 12: nvtxRangePop(); nvtxRangePushA("scb:B3 x c2r (+ all-gather of E when sharded)"); break;
+        case 14: nvtxMarkA("scb:reduce-scatter queued"); break;
+        case 15: nvtxMarkA("scb:all-gather next"); break;
+        case 1: case 3: case 5: case 7: case 13: nvtxRangePop(); break;
+        default: break;
+    }
     if (h->timing && h->ev_ready) cudaEventRecord(h->ev[i], h->stream);
 }
 
@@ -711,6 +732,21 @@ bool z_tma_enabled() {
     return on;
 }
 
+// planes per chunk of the B2 -> B3 hand-over through the L2 (0 = off: one launch each, D through HBM)
+int zchunk_planes(const Plan& pl) {
+    static const int env = [] { const char* e = std::getenv("SCB_ZCHUNK"); return e ? std::atoi(e) : -1; }();
+    if (env >= 0) return env;
+    return 0;
+}
+
+int ensure_chunk_streams(scb_handle* h) {
+    if (h->chunk_stream) return SCB_OK;
+    SCB_CUDA(h, cudaStreamCreateWithFlags(&h->chunk_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&h->ev_chunk_fork, &h->ev_chunk_ready[0], &h->ev_chunk_ready[1], &h->ev_chunk_free[0], &h->ev_chunk_free[1]})
+        SCB_CUDA(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return SCB_OK;
+}
+
 // ---- the convolution -----------------------------------------------------------------------
 // mode 0: free space; mode 1: free space + cathode image (offset_z given); mode 2: general offset
 // phi (optional): scalar potential as a fourth component through the same passes (extension)
@@ -849,42 +885,81 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
         if (!done) SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
     }
     tick(h, 11);
-    {  // B2
-        LinesParams<T> p{};
+    // B2 + B3.  Plain form: B2 writes the y-pruned intermediate D (3A bytes) to HBM and B3 reads it back.  Chunked form
+    // (zchunk planes at a time, SCB_ZCHUNK): B2 of chunk k writes a small ring slot that B3 of chunk k consumes while it
+    // is still in the L2, and that the next chunk but one overwrites before it is ever written back -- D never touches
+    // HBM (algorithmic traffic 3B + 3*Ng*s instead of 3B + 6A + 3*Ng*s).  B2 runs on a side stream, B3 on the handle's
+    // stream, two ring slots, so the tail of one chunk's launch overlaps the head of the next.
+    LinesParams<T> pb2{};
+    pb2.tw = twy;
+    pb2.n_in = pl.L[1];
+    pb2.n_out = pl.n[1];
+    pb2.ninner = pl.ninner;
+    pb2.in_sline = pl.PX;
+    pb2.in_souter = (long long)pl.PX * pl.L[1];
+    pb2.out_sline = pl.PX;
+    pb2.out_souter = (long long)pl.PX * pl.n[1];
+    pb2.in_scomp = (long long)szB;
+    pb2.scale = (T)1;
+    XParams<T> pb3{};
+    pb3.tw = twx;
+    pb3.real_sline = pl.n[0];
+    pb3.n_real = pl.n[0];
+    pb3.PX = pl.PX;
+    pb3.real_scomp = (long long)pl.n[0] * pl.n[1] * pl.n[2];
+    // factr = T(FPEI) (src/solvers/free_space.jl:75) times the inverse-FFT 1/M (:95)
+    pb3.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
+    const int zc = zchunk_planes(pl);
+    if (zc > 0 && 2 * zc <= pl.n[2] && ensure_chunk_streams(h) == SCB_OK) {
+        const size_t plane = (size_t)pl.PX * pl.n[1];          // complex elements of one z plane of D
+        const size_t slot = (size_t)nc * plane * zc;             // one ring slot: nc components x zc planes
+        // the ring lives at the start of D (D itself is not used in this form)
+        SCB_CUDA(h, cudaEventRecord(h->ev_chunk_fork, h->stream));
+        SCB_CUDA(h, cudaStreamWaitEvent(h->chunk_stream, h->ev_chunk_fork, 0));
+        int k = 0;
+        for (int z0 = 0; z0 < pl.n[2]; z0 += zc, ++k) {
+            const int nzc = pl.n[2] - z0 < zc ? pl.n[2] - z0 : zc;
+            C* ring = D + (size_t)(k & 1) * slot;
+            if (k >= 2) SCB_CUDA(h, cudaStreamWaitEvent(h->chunk_stream, h->ev_chunk_free[k & 1], 0));   // slot consumed
+            LinesParams<T> p = pb2;
+            p.in = Cc + (size_t)z0 * pl.PX * pl.L[1];
+            p.out = ring;
+            p.out_scomp = (long long)(plane * zc);
+            SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, nzc, nc, h->chunk_stream));
+            SCB_CUDA(h, cudaEventRecord(h->ev_chunk_ready[k & 1], h->chunk_stream));
+            SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk_ready[k & 1], 0));
+            XParams<T> q = pb3;
+            q.in = ring;
+            q.out = efield + (size_t)z0 * pl.n[0] * pl.n[1];
+            q.nlines = (long long)pl.n[1] * nzc;
+            q.cplx_scomp = (long long)(plane * zc);
+            SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], q, 3, h->stream));
+            if (phi) {
+                q.in = ring + 3 * plane * zc;
+                q.out = phi + (size_t)z0 * pl.n[0] * pl.n[1];
+                SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], q, 1, h->stream));
+            }
+            SCB_CUDA(h, cudaEventRecord(h->ev_chunk_free[k & 1], h->stream));
+        }
+        tick(h, 12);   // (chunked form: B2 and B3 interleave; pass_ms[3] holds both and pass_ms[4] is ~0)
+        h->launches += 2 * k - 2 + (phi ? k : 0);
+    } else {
+        LinesParams<T> p = pb2;
         p.in = Cc;
         p.out = D;
-        p.tw = twy;
-        p.n_in = pl.L[1];
-        p.n_out = pl.n[1];
-        p.ninner = pl.ninner;
-        p.in_sline = pl.PX;
-        p.in_souter = (long long)pl.PX * pl.L[1];
-        p.out_sline = pl.PX;
-        p.out_souter = (long long)pl.PX * pl.n[1];
-        p.in_scomp = (long long)szB;
         p.out_scomp = (long long)szA;
-        p.scale = (T)1;
         SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, pl.n[2], nc, h->stream));
-    }
-    tick(h, 12);
-    {  // B3
-        XParams<T> p{};
-        p.in = D;
-        p.out = efield;
-        p.tw = twx;
-        p.nlines = (long long)pl.n[1] * pl.n[2];
-        p.real_sline = pl.n[0];
-        p.n_real = pl.n[0];
-        p.PX = pl.PX;
-        p.real_scomp = (long long)pl.n[0] * pl.n[1] * pl.n[2];
-        p.cplx_scomp = (long long)szA;
-        // factr = T(FPEI) (src/solvers/free_space.jl:75) times the inverse-FFT 1/M (:95)
-        p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
-        SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
+        tick(h, 12);
+        XParams<T> q = pb3;
+        q.in = D;
+        q.out = efield;
+        q.nlines = (long long)pl.n[1] * pl.n[2];
+        q.cplx_scomp = (long long)szA;
+        SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], q, 3, h->stream));
         if (phi) {  // fourth component -> its own output array, same FPEI / M factor
-            p.in = D + 3 * szA;
-            p.out = phi;
-            SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 1, h->stream));
+            q.in = D + 3 * szA;
+            q.out = phi;
+            SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], q, 1, h->stream));
             h->launches += 1;
         }
     }
@@ -1026,7 +1101,7 @@ int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle
     if (const char* e = std::getenv("SCB_DEPOSIT_MODE")) h->opt.deposit_mode = std::atoi(e);  // tuning knob
     if (const char* e = std::getenv("SCB_PARTICLE_ORDER")) h->opt.particle_order = std::atoi(e);
     if (const char* e = std::getenv("SCB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));  // experiment
-    if (h->opt.particle_order != SCB_ORDER_CELL) h->opt.particle_order = SCB_ORDER_RANDOM;
+    if (h->opt.particle_order != SCB_ORDER_CELL && h->opt.particle_order != SCB_ORDER_CELL_TILE) h->opt.particle_order = SCB_ORDER_RANDOM;
     if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
         return SCB_ERR_ALLOC;
@@ -1043,7 +1118,9 @@ int scb_destroy(scb_handle* h) {
     for (cudaEvent_t e : h->ev_pack) if (e) cudaEventDestroy(e);
     if (h->ev_field) cudaEventDestroy(h->ev_field);
     for (cudaEvent_t e : {h->ev_green_start, h->ev_green_done}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream, h->comm_stream, h->pack_stream, h->green_stream})
+    for (cudaEvent_t e : {h->ev_chunk_fork, h->ev_chunk_ready[0], h->ev_chunk_ready[1], h->ev_chunk_free[0], h->ev_chunk_free[1]})
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t cs : {h->copy_stream, h->d2h_stream, h->comm_stream, h->pack_stream, h->green_stream, h->chunk_stream})
         if (cs) {
             cudaStreamSynchronize(cs);
             cudaStreamDestroy(cs);
@@ -1290,7 +1367,8 @@ int scb_cell_index(scb_handle* h, int64_t np, const void* x, const void* y, cons
 // ---- bunches kept ordered by cell -----------------------------------------------------------------
 int scb_set_particle_order(scb_handle* h, int order) {
     if (!h) return SCB_ERR_INVALID_ARG;
-    if (order != SCB_ORDER_RANDOM && order != SCB_ORDER_CELL) return fail(h, SCB_ERR_INVALID_ARG, "unknown particle order");
+    if (order != SCB_ORDER_RANDOM && order != SCB_ORDER_CELL && order != SCB_ORDER_CELL_TILE)
+        return fail(h, SCB_ERR_INVALID_ARG, "unknown particle order");
     h->opt.particle_order = order;
     return SCB_OK;
 }

@@ -93,9 +93,10 @@ cudaError_t launch_permute(int elem_bytes, long long n, const unsigned* perm, in
 // counters2[0] = sampled neighbour pairs in the same or the x-adjacent cell, counters2[1] = sampled pairs
 cudaError_t launch_order_probe(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const Geom3& g,
                                unsigned long long* counters2, cudaStream_t s);
-// rho must have been cleared (or hold the grid to accumulate into); any particle order is correct
+// rho must have been cleared (or hold the grid to accumulate into); any particle order is correct.  tile: keep a
+// shared-memory tile of rho under the walk (k_deposit_window; measured slower than the plain walk, kept for comparison)
 cudaError_t launch_deposit_runs(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const void* q,
-                                void* rho, const Geom3& g, cudaStream_t s);
+                                void* rho, const Geom3& g, cudaStream_t s, bool tile = false);
 // gathers straight from efield (no node-major copy)
 cudaError_t launch_interpolate_runs(int pdt, int mdt, long long np, const void* x, const void* y, const void* z,
                                     const void* efield, const Geom3& g, void* ex, void* ey, void* ez, cudaStream_t s,

