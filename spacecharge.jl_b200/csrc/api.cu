@@ -1100,7 +1100,6 @@ int scb_create(int device, void* cuda_stream, const scb_options* opt, scb_handle
     if (opt) h->opt = *opt;
     if (const char* e = std::getenv("SCB_DEPOSIT_MODE")) h->opt.deposit_mode = std::atoi(e);  // tuning knob
     if (const char* e = std::getenv("SCB_PARTICLE_ORDER")) h->opt.particle_order = std::atoi(e);
-    if (const char* e = std::getenv("SCB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));  // experiment
     if (h->opt.particle_order != SCB_ORDER_CELL && h->opt.particle_order != SCB_ORDER_CELL_TILE) h->opt.particle_order = SCB_ORDER_RANDOM;
     if (cudaMalloc(&h->d_bounds, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
