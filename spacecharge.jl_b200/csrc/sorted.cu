@@ -614,17 +614,22 @@ __global__ void __launch_bounds__(256, 2) k_deposit_window(long long np, const P
 #ifndef SCB_GR_M
 #define SCB_GR_M 4
 #endif
-// measured at 1e8 particles / 256^3 Float64, cell-ordered (profiles/r02_ab_gather_runs.log): 256 threads x 2 CTAs (128
-// registers, 428 bytes spilled) 1.38 ms; 128 threads x 3 CTAs (168 registers) 1.21 ms; 2 particles per lane 1.77 ms;
-// element stores as results are formed 2.05 ms (partial-sector writes); one thread per particle from L1 1.60 ms
+// measured at 1e8 particles / 256^3 Float64, cell-ordered (profiles/r02_ab_gather_runs.log, first table: no prefetch):
+// 256 threads x 2 CTAs (128 registers, 428 bytes spilled) 1.38 ms; 128 threads x 3 CTAs (168 registers) 1.21 ms;
+// 2 particles per lane 1.77 ms; element stores as results are formed 2.05 ms (partial-sector writes); one thread per
+// particle from L1 1.60 ms.  Second table, with the coordinate prefetch: 128 x 3 (168 registers, 108 bytes spilled)
+// 1.31 ms; 128 x 2 (252 registers, no spill) 1.15 ms; 256 x 1 1.20 ms; prefetch compiled out 1.25 ms
 #ifndef SCB_GR_THREADS
 #define SCB_GR_THREADS 128
 #endif
 #ifndef SCB_GR_MINB
-#define SCB_GR_MINB 3
+#define SCB_GR_MINB 2
 #endif
 #ifndef SCB_GR_STORE_NOW
 #define SCB_GR_STORE_NOW 0
+#endif
+#ifndef SCB_GR_PREFETCH
+#define SCB_GR_PREFETCH 1
 #endif
 constexpr int GR_M = SCB_GR_M;
 
@@ -699,24 +704,38 @@ __global__ void __launch_bounds__(SCB_GR_THREADS, SCB_GR_MINB) k_interpolate_run
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1], sc = sz * g.n[2];
-    for (long long wbase = warp * PER_WARP; wbase < np; wbase += nwarps * PER_WARP) {
+    // coordinates of the warp's next group are requested before the current group is worked on: ncu on the version
+    // without it showed 4.2 long-scoreboard stalls per issued instruction at 12 warps per SM (every iteration exposed
+    // the DRAM round trip of its three coordinate loads)
+    auto load_group = [&](long long wb, P (&a)[GR_M], P (&b)[GR_M], P (&c)[GR_M]) {
+        const long long j0 = wb + lane * GR_M;
+        if (VEC && wb + PER_WARP <= np) {
+            ld4(x + j0, a);
+            ld4(y + j0, b);
+            ld4(z + j0, c);
+        } else {
+            const int m = (int)(np - j0 >= GR_M ? GR_M : (np - j0 > 0 ? np - j0 : 0));
+#pragma unroll
+            for (int j = 0; j < GR_M; ++j) {
+                const bool ok = j < m;
+                a[j] = ok ? ld_stream(x + j0 + j) : (P)0;
+                b[j] = ok ? ld_stream(y + j0 + j) : (P)0;
+                c[j] = ok ? ld_stream(z + j0 + j) : (P)0;
+            }
+        }
+    };
+    P px[GR_M], py[GR_M], pz[GR_M];
+    long long wbase = warp * PER_WARP;
+    if (wbase < np) load_group(wbase, px, py, pz);
+    for (; wbase < np; wbase += nwarps * PER_WARP) {
         const long long i0 = wbase + lane * GR_M;
         const bool full = wbase + PER_WARP <= np;   // warp-uniform
         const int cnt = (int)(np - i0 >= GR_M ? GR_M : (np - i0 > 0 ? np - i0 : 0));
-        P px[GR_M], py[GR_M], pz[GR_M];
-        if (VEC && full) {
-            ld4(x + i0, px);
-            ld4(y + i0, py);
-            ld4(z + i0, pz);
-        } else {
+        const long long wnext = wbase + nwarps * PER_WARP;
+        P qx[GR_M], qy[GR_M], qz[GR_M];
 #pragma unroll
-            for (int j = 0; j < GR_M; ++j) {
-                const bool ok = j < cnt;
-                px[j] = ok ? ld_stream(x + i0 + j) : (P)0;
-                py[j] = ok ? ld_stream(y + i0 + j) : (P)0;
-                pz[j] = ok ? ld_stream(z + i0 + j) : (P)0;
-            }
-        }
+        for (int j = 0; j < GR_M; ++j) qx[j] = qy[j] = qz[j] = (P)0;
+        if (SCB_GR_PREFETCH && wnext < np) load_group(wnext, qx, qy, qz);
         P ox[GR_M], oy[GR_M], oz[GR_M];
         constexpr bool NOW = SCB_GR_STORE_NOW != 0;
         if (VEC && full && !kick.on) {
@@ -729,6 +748,12 @@ __global__ void __launch_bounds__(SCB_GR_THREADS, SCB_GR_MINB) k_interpolate_run
         } else {
             // tail of the bunch, unaligned arrays, fused momentum kick (p <- p + coef * E): element stores
             walk_gather<P, T, W, false, true>(px, py, pz, cnt, g, e, sy, sz, sc, ox, oy, oz, kick, ex + i0, ey + i0, ez + i0);
+        }
+        if (SCB_GR_PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < GR_M; ++j) { px[j] = qx[j]; py[j] = qy[j]; pz[j] = qz[j]; }
+        } else if (wnext < np) {
+            load_group(wnext, px, py, pz);
         }
     }
 }
