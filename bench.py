@@ -262,10 +262,16 @@ def cell_ordered_regime(scb, mesh, x, y, z, q, ex, ey, ez, at_cathode, stage_ran
         scb.set_particle_order(mesh, "random")
     ab = algorithmic_bytes(n_local, grid, s, at_cathode)
     roof = {}
+    traffic = {}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture (config 5)
+    if os.path.exists(tr) and world == 1 and n_local == 100_000_000 and tuple(grid) == (256, 256, 256):
+        with open(tr) as f:
+            traffic = json.load(f).get("large_%s_cell_ordered" % ("f64" if s == 8 else "f32"), {})
     for k in ("deposit", "interpolate"):
         gbs = ab[k] / (ordered[k] * 1e-3) / 1e9
+        name = "k_deposit_runs" if k == "deposit" else "k_interpolate_runs"
         roof[k] = {"ms": round(ordered[k], 4), "alg_MB": round(ab[k] / 1e6, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4),
-                   "kernel": "k_deposit_runs" if k == "deposit" else "k_interpolate_runs"}
+                   "kernel": name, "bound": "hbm", "traffic": traffic.get(name)}
     step_random = stage_random["deposit"] + stage_random["solve"] + stage_random["interpolate"]
     gain = step_random - ordered["step"]
     resort = t_sort1 + t_perm1
