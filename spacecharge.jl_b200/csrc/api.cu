@@ -1061,9 +1061,12 @@ int prefetch_green(scb_handle* h, int mdt, const int64_t n[3], const double min_
     if (rc == SCB_OK && at_cathode) rc = get_green(h, pl, kimg, &unused);
     h->stream = main_stream;
     h->timing = timing;
+    // Recorded even when a build failed half-way: whatever WAS built and cached (e.g. the free-space spectrum when the
+    // image spectrum failed) was built on green_stream, and the next solve that finds it in the cache has to wait for it.
+    const cudaError_t ev = cudaEventRecord(h->ev_green_done, h->green_stream);
+    if (ev == cudaSuccess) h->green_pending = true;
     if (rc != SCB_OK) return rc;
-    SCB_CUDA(h, cudaEventRecord(h->ev_green_done, h->green_stream));
-    h->green_pending = true;
+    if (ev != cudaSuccess) return cuda_fail(h, ev, "cudaEventRecord(ev_green_done)");
     return SCB_OK;
 }
 

@@ -61,6 +61,15 @@ def _worker(rank, world, port, out_dir):
                     if rank == 0:
                         print("world %d grid %s cathode %d sharded %d: E%d vs oracle %.2e, vs one GPU %.2e"
                               % (world, grid, cath, sharded, c, err, float((a - r).abs().max() / r.abs().max())), flush=True)
+            if not sharded and grid[0] <= 32:
+                # two deposits into one grid (clear=False, e.g. two species): in the replicated mode rho holds the sum
+                # over the ranks after every call, so only the SECOND call's contribution may be reduced again
+                half = mine[0].numel() // 2
+                scb.deposit_(mesh, *[t[:half] for t in mine])
+                scb.deposit_(mesh, *[t[half:] for t in mine], clear=False)
+                torch.cuda.synchronize()
+                err = float((mesh.rho - ref.rho).abs().max() / ref.rho.abs().max())
+                assert err < max(tol, 1e-13), (grid, "two-species deposit with clear=False over ranks", err)
             # fused step; in the sharded mode also with the field slabs broadcast and gathered in overlapping passes
             for overlap in ("0", "1"):
                 os.environ["SCB_GATHER_OVERLAP"] = overlap
