@@ -489,13 +489,22 @@ def solve_potential_(mesh: Mesh3D, at_cathode: bool = False) -> None:
     computed with the reference's ``potential_green_function`` (src/green_functions.jl:13-22) as a fourth
     component of the same fused convolution.  ``mesh.efield`` is written exactly as by ``solve_``."""
     torch = _torch()
-    if mesh.sharded:
-        raise ErrorException("solve_potential_ is single-GPU (the slab-decomposed solve returns E only)")
     hd = mesh.handle
     hd.use_current_stream()
     if mesh._phi is None:
         mesh._phi = torch.zeros_like(mesh._rho)
-    hd.check(hd.lib.scb_solve_potential(hd.h, mesh._rho.data_ptr(), mesh._efield.data_ptr(), mesh._phi.data_ptr(),
+    rho = mesh._rho
+    if mesh.sharded:
+        # the slab-decomposed solve carries E only; for the potential the partial grids are summed into a scratch copy
+        # and every rank runs the four-component solve on the full grid (mesh.rho keeps this rank's partial grid)
+        import torch.distributed as dist
+        rho = mesh._rho.clone()
+        if dist.get_backend(mesh.group) == "nccl":
+            hd.init_comm(mesh.group)
+            hd.check(hd.lib.scb_allreduce_rho(hd.h, rho.data_ptr(), mesh._n(), mesh._mdt()))
+        else:
+            dist.all_reduce(rho, op=dist.ReduceOp.SUM, group=mesh.group)
+    hd.check(hd.lib.scb_solve_potential(hd.h, rho.data_ptr(), mesh._efield.data_ptr(), mesh._phi.data_ptr(),
                                         mesh._mdt(), mesh._n(), mesh._lo(), mesh._hi(), mesh._d(), float(mesh.gamma),
                                         1 if at_cathode else 0))
 

@@ -61,6 +61,15 @@ def _worker(rank, world, port, out_dir):
                     if rank == 0:
                         print("world %d grid %s cathode %d sharded %d: E%d vs oracle %.2e, vs one GPU %.2e"
                               % (world, grid, cath, sharded, c, err, float((a - r).abs().max() / r.abs().max())), flush=True)
+            if grid[0] <= 32 and T == np.float64:
+                # scalar potential on a particle-sharded mesh (extension): equals the single-GPU potential
+                scb.deposit_(ref, *full)
+                scb.solve_potential_(ref, at_cathode=cath)
+                scb.deposit_(mesh, *mine)
+                scb.solve_potential_(mesh, at_cathode=cath)
+                torch.cuda.synchronize()
+                err = float((mesh.phi - ref.phi).abs().max() / ref.phi.abs().max())
+                assert err < 1e-11, (grid, cath, sharded, "phi", err)
             if not sharded and grid[0] <= 32:
                 # two deposits into one grid (clear=False, e.g. two species): in the replicated mode rho holds the sum
                 # over the ranks after every call, so only the SECOND call's contribution may be reduced again
