@@ -331,7 +331,8 @@ def main(print=print):
         "l2": "inputs larger than L2 (particle arrays %.1f GB per step)" % (4 * npart * s / 1e9),
         "parallelism": ("single GPU" if world == 1 else
                         "particles sharded over %d GPUs; rho reduce-scattered into z slabs, slab-decomposed FFT solve "
-                        "(NCCL all-to-all pencil transposes), E all-gathered" % world)}
+                        "(pencil transposes z slabs <-> kx slabs fused into the x / y passes over NVLink peer memory), "
+                        "E all-gathered" % world)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -526,11 +527,15 @@ def main(print=print):
             gbs = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
             coll[k] = {"ms": round(ms_k, 4), "bound": "nvlink", "bytes_per_gpu_MB": round(bytes_k / 1e6, 1), "GBps": round(gbs, 1),
                        "peak": NVLINK_GBS, "frac": round(gbs / NVLINK_GBS, 4)}
-        # the two pencil transposes are fused into F2 and Z (peer-memory stores): their remote bytes, for the record
-        coll["transposes_fused_into_F2_and_Z"] = {
-            "F2_remote_MB_per_gpu": round((world - 1) / world * b_slab / world / 1e6, 1),
-            "Z_remote_MB_per_gpu": round((world - 1) / world * 3 * b_slab / world / 1e6, 1),
-            "note": "F2 / Z stage times include these stores and the rank barrier that follows; bound = max(HBM, NVLink)"}
+        # the two pencil transposes are fused into the producing kernels (peer-memory stores): their remote bytes, for
+        # the record.  kx-slab solve (default): F1 sends A/G, B2 sends 3A/G per rank; ky-slab solve (SCB_SHARD=ky): F2
+        # sends B/G, the z pass 3B/G (B = 2A)
+        a_slab = full["F1"] - ng_b
+        ky = os.environ.get("SCB_SHARD", "") == "ky"
+        coll["transposes_fused_into_%s" % ("F2_and_Z" if ky else "F1_and_B2")] = {
+            "forward_remote_MB_per_gpu": round((world - 1) / world * (b_slab if ky else a_slab) / world / 1e6, 1),
+            "back_remote_MB_per_gpu": round((world - 1) / world * 3 * (b_slab if ky else a_slab) / world / 1e6, 1),
+            "note": "the stage times of those kernels include the stores and the rank barrier that follows; bound = max(HBM, NVLink)"}
     stage_roof = {}
     for k in ("deposit", "interpolate", "F1", "F2", "Z", "B2", "B3"):
         gbs = ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0
@@ -539,7 +544,7 @@ def main(print=print):
     kernel_names = {"deposit": "k_deposit_tiles" if n_local >= grid[0] * grid[1] * grid[2] else "k_deposit_pair",
                     "interpolate": "k_interpolate_pair2_f64" if s == 8 else "k_interpolate_packed_f32",
                     "F1": "k_x_r2c", "F2": "k_lines<-1>",
-                    "Z": ("k_z_eo" if (world == 1 and not at_cathode and 128 < grid[2] <= 256) else
+                    "Z": ("k_z_eo" if (not at_cathode and 128 < grid[2] <= 256 and os.environ.get("SCB_SHARD", "") != "ky") else
                           "k_z_tma" if (world == 1 and not at_cathode and grid[2] <= 256) else "k_z_fused"),
                     "B2": "k_lines<+1>", "B3": "k_x_c2r"}
     # dominant STAGE of the step, collectives included: at 8 GPUs it is a collective, and the line says so

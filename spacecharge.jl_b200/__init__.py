@@ -293,13 +293,13 @@ class Mesh3D:
         # slab-decomposed solve (scb_solve_sharded) when the grid divides over the ranks; otherwise
         # rho is all-reduced and the solve replicated.  In the sharded mode mesh.rho holds this
         # rank's PARTIAL charge grid after deposit_ (call reduce_rho_() to materialise the sum).
-        # sharded_solve=None picks by rank count: on two GPUs the replicated solve is faster (measured, config 5:
-        # 4.76 ms against 4.99 ms per step -- half of the three-component spectrum crosses NVLink in the transposes),
-        # from four GPUs on the slab-decomposed solve wins (8 GPUs: 2.45 ms against 4.15 ms).
+        # sharded_solve=None: the slab-decomposed solve whenever the grid divides over the ranks.  (Round 1 cut the
+        # spectrum into ky slabs and was slower than the replicated solve on two GPUs; the kx-slab exchange of round 2
+        # moves half the bytes and runs the z pass locally: 4.41 ms against 4.64 ms replicated on two GPUs, config 5.)
         self.sharded = False
         if group is not None and sharded_solve is None:
             import torch.distributed as dist
-            sharded_solve = dist.get_world_size(group) >= 4
+            sharded_solve = dist.get_world_size(group) >= 2
         if group is not None and sharded_solve:
             import torch.distributed as dist
             w = dist.get_world_size(group)

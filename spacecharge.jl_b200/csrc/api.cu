@@ -747,6 +747,57 @@ int ensure_chunk_streams(scb_handle* h) {
     return SCB_OK;
 }
 
+// The fused z pass on data of pitch p.PX (the full PX on one GPU, PX / ranks in the kx-slab solve): the even/odd-bin
+// kernel when it applies (free space, padded z length 512), else the TMA kernel (free space, nz <= 256), else k_z_fused
+// (cathode image, general offset, long z).  `p` arrives with everything but the tensor maps' business filled in.
+template <typename T>
+int launch_z_pass(scb_handle* h, const Plan& pl, ZParams<T>& p, int mode, const GreenEntry* gfree, const cx_t<T>* B,
+                  cx_t<T>* Cc, size_t comp_stride, int nc) {
+    const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
+    const bool f64 = sizeof(T) == 8;
+    const cuuint64_t s = sizeof(T), PX = p.PX, L1 = pl.L[1], nz = pl.n[2];
+    if (mode == 0 && z_eo_enabled() && z_eo_eligible(pl) && gfree->t_off && gfree->PZ == ZEoLayout<T>::PZ) {
+        // even/odd-bin variant: one warp per line, 256-point transforms with a single exchange (see k_z_eo)
+        const cuuint32_t TX = ZEoLayout<T>::TX;
+        const int rowb = ZEoLayout<T>::ROWB;
+        const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        CUtensorMap mB, mC;
+        const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
+        const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
+        const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)comp_stride * 2 * s};
+        const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
+        if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB, swz) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC, swz)) {
+            p.St = reinterpret_cast<const T*>(static_cast<const char*>(gfree->data) + gfree->t_off);
+            p.PZ = gfree->PZ;
+            SCB_CUDA(h, launch_z_eo<T>(p, mB, mC, h->stream));
+            return SCB_OK;
+        }
+    }
+    if (mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
+        // all global traffic of the pass through the TMA unit (see k_z_tma)
+        const cuuint32_t TX = (cuuint32_t)tz_for(pl.L[2]);
+        const cuuint64_t PXg = pl.PX, Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
+        CUtensorMap mB, mC, mS;
+        const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
+        const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
+        const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)comp_stride * 2 * s};
+        const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
+        const cuuint64_t dS[4] = {PXg, Lyh1, Lzh1, (cuuint64_t)gfree->ncomp},
+                         sS[3] = {PXg * s, PXg * Lyh1 * s, (cuuint64_t)gfree->scomp * s};
+        const cuuint32_t bS[4] = {TX, 1, (cuuint32_t)z_tma_srows<T>(pl.L[2]), 1};
+        if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC) &&
+            make_tensor_map(&mS, f64, 4, gfree->data, dS, sS, bS)) {
+            cudaError_t e = launch_z_tma<T>(pl.L[2], p, mB, mC, mS, h->stream);
+            if (e == cudaSuccess) return SCB_OK;
+            if (e != cudaErrorNotSupported) return cuda_fail(h, e, "launch_z_tma");
+            (void)cudaGetLastError();
+        }
+    }
+    SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
+    return SCB_OK;
+}
+
 // ---- the convolution -----------------------------------------------------------------------
 // mode 0: free space; mode 1: free space + cathode image (offset_z given); mode 2: general offset
 // phi (optional): scalar potential as a fourth component through the same passes (extension)
@@ -838,51 +889,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
             p.H = static_cast<const C*>(gaux->data);
             p.H_scomp = gaux->scomp;
         }
-        const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
-        bool done = false;
-        if (mode == 0 && z_eo_enabled() && z_eo_eligible(pl) && gfree->t_off && gfree->PZ == ZEoLayout<T>::PZ) {
-            // even/odd-bin variant: one warp per line, 256-point transforms with a single exchange (see k_z_eo)
-            const bool f64 = sizeof(T) == 8;
-            const cuuint64_t s = sizeof(T), PX = pl.PX, L1 = pl.L[1], nz = pl.n[2];
-            const cuuint32_t TX = ZEoLayout<T>::TX;
-            const int rowb = ZEoLayout<T>::ROWB;
-            const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                           : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-            CUtensorMap mB, mC;
-            const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
-            const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
-            const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)szB * 2 * s};
-            const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
-            if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB, swz) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC, swz)) {
-                p.St = reinterpret_cast<const T*>(static_cast<const char*>(gfree->data) + gfree->t_off);
-                p.PZ = gfree->PZ;
-                SCB_CUDA(h, launch_z_eo<T>(p, mB, mC, h->stream));
-                done = true;
-            }
-        }
-        if (!done && mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
-            // all global traffic of the pass through the TMA unit (see k_z_tma)
-            const bool f64 = sizeof(T) == 8;
-            const cuuint64_t s = sizeof(T), PX = pl.PX, L1 = pl.L[1], nz = pl.n[2];
-            const cuuint32_t TX = (cuuint32_t)tz_for(pl.L[2]);
-            const cuuint64_t Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
-            CUtensorMap mB, mC, mS;
-            const cuuint64_t dB[3] = {2 * PX, L1, nz}, sB[2] = {2 * PX * s, 2 * PX * L1 * s};
-            const cuuint32_t bB[3] = {2 * TX, 1, (cuuint32_t)nz};
-            const cuuint64_t dC[4] = {2 * PX, L1, nz, (cuuint64_t)nc}, sC[3] = {2 * PX * s, 2 * PX * L1 * s, (cuuint64_t)szB * 2 * s};
-            const cuuint32_t bC[4] = {2 * TX, 1, (cuuint32_t)nz, 1};
-            const cuuint64_t dS[4] = {PX, Lyh1, Lzh1, (cuuint64_t)gfree->ncomp},
-                             sS[3] = {PX * s, PX * Lyh1 * s, (cuuint64_t)gfree->scomp * s};
-            const cuuint32_t bS[4] = {TX, 1, (cuuint32_t)z_tma_srows<T>(pl.L[2]), 1};
-            if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC) &&
-                make_tensor_map(&mS, f64, 4, gfree->data, dS, sS, bS)) {
-                cudaError_t e = launch_z_tma<T>(pl.L[2], p, mB, mC, mS, h->stream);
-                if (e == cudaSuccess) done = true;
-                else if (e != cudaErrorNotSupported) return cuda_fail(h, e, "launch_z_tma");
-                else (void)cudaGetLastError();
-            }
-        }
-        if (!done) SCB_CUDA(h, launch_z_fused<T>(pl.L[2], kind, p, h->stream));
+        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, B, Cc, szB, nc));
     }
     tick(h, 11);
     // B2 + B3.  Plain form: B2 writes the y-pruned intermediate D (3A bytes) to HBM and B3 reads it back.  Chunked form
@@ -1779,9 +1786,157 @@ int all_to_all(scb_handle* h, const char* send, char* recv, size_t block_bytes, 
     return SCB_OK;
 }
 
+// Which axis the slab-decomposed solve cuts between the x pass and the y / z passes.
+//   kx (default, round 2): after F1 the z slabs are exchanged for kx slabs (every rank: all y, all z, PX / ranks kx), F2,
+//       the z pass and B2 run entirely locally -- the z pass with the single-GPU kernels (k_z_eo / k_z_tma) -- and the
+//       y-PRUNED result goes back to z slabs for B3.  Bytes on the links per rank: (A + 3A) / G * (G-1)/G.
+//   ky (round 1): F1 and F2 on z slabs, exchange for ky slabs, z pass, back.  (B + 3B) / G * (G-1)/G with B = 2A, the
+//       z pass stores to peers element by element.  Needs the padded y length divisible by the ranks.
+bool shard_by_kx(const scb_handle* h, const Plan& pl) {
+    static const int want_ky = [] { const char* e = std::getenv("SCB_SHARD"); return e && (e[0] == 'k' && e[1] == 'y'); }();
+    const bool kx_ok = pl.PX % h->nranks == 0, ky_ok = pl.L[1] % h->nranks == 0;
+    return kx_ok && !(want_ky && ky_ok);
+}
+
+template <typename T>
+int run_solve_sharded_kx(scb_handle* h, const T* rho_partial, T* efield, const Plan& pl, const double delta[3], double gamma,
+                         int mode, const double offset[3], bool defer_gather) {
+    using C = cx_t<T>;
+    const int G = h->nranks, me = h->rank;
+    const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
+    const ncclDataType_t nt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+    const int nzl = pl.n[2] / G, PXl = pl.PX / G;
+    const int kx0 = me * PXl;
+    const int ninl = pl.ninner - kx0 < 0 ? 0 : (pl.ninner - kx0 < PXl ? pl.ninner - kx0 : PXl);   // valid kx of this rank
+    const double zero3[3] = {0, 0, 0};
+    const GreenEntry* gfree = nullptr;
+    const GreenEntry* gaux = nullptr;
+    h->t_green = false;
+    SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, zero3, mdt, 0), &gfree));
+    if (mode == 1) {
+        SCB_TRY(get_green(h, pl, make_key(pl, delta, gamma, offset, mdt, 1), &gaux));
+        for (auto& e : h->green)
+            if (e.key == make_key(pl, delta, gamma, zero3, mdt, 0)) gfree = &e;
+    }
+    if (h->green_pending) {
+        SCB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_green_done, 0));
+        h->green_pending = false;
+    }
+    const size_t slab_elems = (size_t)pl.n[0] * pl.n[1] * nzl;
+    if (h->slab_bytes < slab_elems * sizeof(T)) {
+        if (h->slab) { SCB_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(h->slab); h->slab = nullptr; h->slab_bytes = 0; }
+        if (cudaMalloc(&h->slab, slab_elems * sizeof(T)) != cudaSuccess) { (void)cudaGetLastError(); return fail(h, SCB_ERR_ALLOC, "slab allocation failed"); }
+        h->slab_bytes = slab_elems * sizeof(T);
+    }
+    T* slab = static_cast<T*>(h->slab);
+    const size_t a1 = (size_t)PXl * pl.n[1] * pl.n[2];   // [z][y][kx_l]
+    const size_t b1 = (size_t)PXl * pl.L[1] * pl.n[2];   // [z][ky][kx_l]
+    const size_t blk = (size_t)PXl * pl.n[1] * nzl;      // one (rank, rank) block of the exchanges
+    SCB_TRY(ensure_sh_arena(h, (8 * a1 + 4 * b1) * sizeof(C)));
+    SCB_TRY(exchange_arenas(h));
+    const bool p2p = h->p2p == 1;
+    C* base = static_cast<C*>(h->sh_arena);
+    C* A1 = base;                 // received x spectra of ALL z, this rank's kx block
+    C* S1 = A1 + a1;              // NCCL fallback: F1 output blocked by destination rank
+    C* B1 = S1 + a1;              // after F2
+    C* C1 = B1 + b1;              // after the z pass, 3 components
+    C* DS = C1 + 3 * b1;          // NCCL fallback: B2 output (natural order = blocked by destination rank), 3 components
+    C* DR = DS + 3 * a1;          // received for B3: [component][source rank][z_l][y][kx_l]
+    const C *twx, *twy, *twz;
+    SCB_TRY(get_twiddles<T>(h, pl.L[0], &twx));
+    SCB_TRY(get_twiddles<T>(h, pl.L[1], &twy));
+    SCB_TRY(get_twiddles<T>(h, pl.L[2], &twz));
+
+    tick(h, 8);
+    SCB_NCCL(h, g_nccl.ReduceScatter(rho_partial, slab, slab_elems, nt, ncclSum, h->comm, h->stream));
+    tick(h, 14);
+    {  // F1 on the z slab; every bin goes straight to the rank that owns its kx block
+        XParams<T> p{};
+        p.in = slab; p.out = S1; p.tw = twx;
+        p.nlines = (long long)pl.n[1] * nzl; p.real_sline = pl.n[0]; p.n_real = pl.n[0]; p.PX = pl.PX; p.scale = (T)1;
+        p.split = PXl;
+        if (p2p) {
+            p.line0 = (long long)me * pl.n[1] * nzl;
+            for (int r = 0; r < G; ++r) p.out_peer[r] = static_cast<C*>(h->peer_arena[r]) + (A1 - base);
+        } else {
+            p.line0 = 0;
+            for (int r = 0; r < G; ++r) p.out_peer[r] = S1 + (size_t)r * blk;
+        }
+        SCB_CUDA(h, launch_x_r2c<T>(pl.L[0], p, 1, h->stream));
+    }
+    if (p2p) SCB_TRY(rank_barrier(h));
+    else SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(S1), reinterpret_cast<char*>(A1), blk * sizeof(C), 1, 0));
+    tick(h, 9);
+    if (ninl > 0) {  // F2, local
+        LinesParams<T> p{};
+        p.in = A1; p.out = B1; p.tw = twy;
+        p.n_in = pl.n[1]; p.n_out = pl.L[1]; p.ninner = ninl;
+        p.in_sline = PXl; p.in_souter = (long long)PXl * pl.n[1];
+        p.out_sline = PXl; p.out_souter = (long long)PXl * pl.L[1];
+        p.scale = (T)1;
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], -1, p, pl.n[2], 1, h->stream));
+    }
+    tick(h, 10);
+    if (ninl > 0) {  // z pass, local, with the single-GPU kernels
+        ZParams<T> p{};
+        p.in = B1; p.out = C1; p.tw = twz;
+        p.out_scomp = (long long)b1;
+        p.nz = pl.n[2]; p.ncomp = 3; p.ninner = ninl; p.PX = PXl;
+        p.Ly = pl.L[1]; p.Lyg = pl.L[1]; p.ky0 = 0;
+        p.kx0 = kx0; p.ninner_g = pl.ninner; p.PXg = pl.PX;
+        p.S = static_cast<const T*>(gfree->data); p.S_scomp = gfree->scomp;
+        if (gaux) { p.H = static_cast<const C*>(gaux->data); p.H_scomp = gaux->scomp; }
+        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, B1, C1, b1, 3));
+    }
+    tick(h, 11);
+    if (ninl > 0) {  // B2, local; plane z goes to the owner of its z slab, into the block reserved for this rank
+        LinesParams<T> p{};
+        p.in = C1; p.tw = twy;
+        p.n_in = pl.L[1]; p.n_out = pl.n[1]; p.ninner = ninl;
+        p.in_sline = PXl; p.in_souter = (long long)PXl * pl.L[1]; p.in_scomp = (long long)b1;
+        p.out_sline = PXl; p.out_souter = (long long)PXl * pl.n[1]; p.out_scomp = (long long)a1;
+        p.scale = (T)1;
+        if (p2p) {
+            p.use_peers = 2;
+            p.out_osplit = nzl;
+            p.out = DR;
+            for (int r = 0; r < G; ++r) p.out_peer[r] = static_cast<C*>(h->peer_arena[r]) + (DR - base) + (size_t)me * blk;
+        } else {
+            p.out = DS;
+        }
+        SCB_CUDA(h, launch_lines<T>(pl.L[1], +1, p, pl.n[2], 3, h->stream));
+    }
+    if (p2p) SCB_TRY(rank_barrier(h));
+    else SCB_TRY(all_to_all(h, reinterpret_cast<const char*>(DS), reinterpret_cast<char*>(DR), blk * sizeof(C), 3, a1 * sizeof(C)));
+    tick(h, 12);
+    const long long ng = (long long)pl.n[0] * pl.n[1] * pl.n[2];
+    {  // B3 on the z slab, kx gathered from the ranks' blocks, straight into this rank's slab of the full field
+        XParams<T> p{};
+        p.in = DR; p.out = efield + (size_t)me * slab_elems; p.tw = twx;
+        p.nlines = (long long)pl.n[1] * nzl; p.real_sline = pl.n[0]; p.n_real = pl.n[0]; p.PX = pl.PX;
+        p.real_scomp = ng; p.cplx_scomp = (long long)a1;
+        p.split = PXl; p.sblock = (long long)blk;
+        p.scale = (T)(kFPEI / ((double)pl.L[0] * pl.L[1] * pl.L[2]));
+        SCB_CUDA(h, launch_x_c2r<T>(pl.L[0], p, 3, h->stream));
+    }
+    tick(h, 15);
+    if (!defer_gather) {
+        SCB_NCCL(h, g_nccl.GroupStart());
+        for (int c = 0; c < 3; ++c)
+            SCB_NCCL(h, g_nccl.AllGather(efield + c * ng + (size_t)me * slab_elems, efield + c * ng, slab_elems, nt, h->comm, h->stream));
+        SCB_NCCL(h, g_nccl.GroupEnd());
+    }
+    tick(h, 13);
+    h->t_pass = true;
+    h->t_coll = true;
+    h->launches += 5 + 4;
+    return SCB_OK;
+}
+
 template <typename T>
 int run_solve_sharded(scb_handle* h, const T* rho_partial, T* efield, const Plan& pl, const double delta[3], double gamma,
                       int mode, const double offset[3], bool defer_gather = false) {
+    if (shard_by_kx(h, pl)) return run_solve_sharded_kx<T>(h, rho_partial, efield, pl, delta, gamma, mode, offset, defer_gather);
     using C = cx_t<T>;
     const int G = h->nranks, me = h->rank;
     const int mdt = sizeof(T) == 8 ? SCB_F64 : SCB_F32;
@@ -2040,8 +2195,8 @@ int scb_solve_sharded(scb_handle* h, const void* rho_partial, void* efield, int 
         return fail(h, SCB_ERR_INVALID_ARG, "bad argument to scb_solve_sharded");
     SCB_TRY(check_grid(h, n));
     const Plan pl = make_plan(n);
-    if (pl.n[2] % h->nranks != 0 || pl.L[1] % h->nranks != 0)
-        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the padded y length must be multiples of the number of ranks");
+    if (pl.n[2] % h->nranks != 0 || (pl.PX % h->nranks != 0 && pl.L[1] % h->nranks != 0))
+        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the spectrum pitch (or the padded y length) must be multiples of the number of ranks");
     SCB_CUDA(h, cudaSetDevice(h->device));
     double offset[3] = {0.0, 0.0, 0.0};
     if (at_cathode) offset[2] = image_offset_z(mdt, min_bounds[2], max_bounds[2]);
@@ -2067,8 +2222,8 @@ int scb_step_sharded(scb_handle* h, int64_t np, const void* x, const void* y, co
     if (np > 0 && (!x || !y || !z || !q || !ex || !ey || !ez)) return fail(h, SCB_ERR_INVALID_ARG, "null particle array");
     SCB_TRY(check_grid(h, n));
     const Plan pl = make_plan(n);
-    if (pl.n[2] % h->nranks != 0 || pl.L[1] % h->nranks != 0)
-        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the padded y length must be multiples of the number of ranks");
+    if (pl.n[2] % h->nranks != 0 || (pl.PX % h->nranks != 0 && pl.L[1] % h->nranks != 0))
+        return fail(h, SCB_ERR_UNSUPPORTED, "nz and the spectrum pitch (or the padded y length) must be multiples of the number of ranks");
     // Opt-in (SCB_GATHER_OVERLAP=1, read on every call).  Measured on 2 GPUs at config 5: 6.38 ms per step against 5.11 ms
     // for the plain sequence -- one-root broadcasts give up the all-links parallelism of the all-gather, and a filtered
     // gather pass costs almost a full pass (every warp iteration still pays its latency) -- see DESIGN.md section 4.

@@ -70,7 +70,10 @@ struct LinesParams {
     long long in_sblock, out_sblock;
     // peer-memory variant of the output split: block b is stored through out_peer[b] (a pointer into
     // rank b's receive buffer, mapped over NVLink) -- the all-to-all is fused into the pass
+    // use_peers == 2: the peer is chosen by the OUTER index instead (kx-slab solve, B2: plane z goes to the owner of its
+    // z slab): outer o is stored through out_peer[o / out_osplit] at outer index o % out_osplit
     int use_peers;
+    int out_osplit;
     cx_t<T>* out_peer[SCB_MAX_RANKS];
     // input known to be even (fold_sign = +1) or odd (-1) about index 0 (mod N): only positions
     // 0..N/2 are stored, position pos > N/2 is read as fold_sign * in[N - pos]
@@ -114,14 +117,18 @@ __global__ void __launch_bounds__(tx_for(N) * (N / 8)) k_lines(const LinesParams
         }
     }
     fft_line<T, N, DIR>(v, lay, j, p.tw);
-    const long long dst_off = (long long)blockIdx.z * p.out_scomp + (long long)blockIdx.y * p.out_souter + kx;
+    const int outer = p.use_peers == 2 ? (int)blockIdx.y % p.out_osplit : (int)blockIdx.y;
+    const long long dst_off = (long long)blockIdx.z * p.out_scomp + (long long)outer * p.out_souter + kx;
+    C* const outer_peer = p.use_peers == 2 ? p.out_peer[blockIdx.y / p.out_osplit] : nullptr;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int pos = j + q * TPL;
         if (valid && pos < p.n_out) {
             C o = cscale(v[q], p.scale);
             if (p.out_rot) o = cmake<C>(o.y, -o.x);
-            if (p.use_peers)
+            if (p.use_peers == 2)
+                outer_peer[dst_off + (long long)pos * p.out_sline] = o;
+            else if (p.use_peers)
                 p.out_peer[pos / p.out_split][dst_off + (long long)(pos % p.out_split) * p.out_sline] = o;
             else
                 p.out[dst_off + line_offset<T>(pos, p.out_sline, p.out_split, p.out_sblock)] = o;
@@ -141,6 +148,9 @@ struct ZParams {
     int ncomp;              // 3: Ex,Ey,Ez; 4: + scalar potential (component 3, even Green function => real spectrum)
     int ninner, PX, Ly;     // Ly: ky lines held by this rank (= plane pitch / PX)
     int Lyg, ky0;           // global padded y length and first global ky of this rank (Lyg = Ly, ky0 = 0 on one GPU)
+    // kx-slab solve (multi-GPU): this rank holds kx in [kx0, kx0 + ninner) with pitch PX; the Green spectrum keeps the
+    // global extents ninner_g / pitch PXg.  One GPU and the ky-slab solve: kx0 = 0, ninner_g = ninner, PXg = PX.
+    int kx0, ninner_g, PXg;
     // peer-memory output (multi-GPU): z plane pos goes to rank pos / out_split through out_peer[rank],
     // at local plane pos % out_split -- the all-to-all back is fused into the pass
     int use_peers, out_split;
@@ -201,12 +211,12 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
     auto prefetch_S = [&](int c) {
         if constexpr (USE_S) {
             if (valid) {
-                const T* base = p.S + c * p.S_scomp + kx + (long long)p.PX * kyf;
+                const T* base = p.S + c * p.S_scomp + (kx + p.kx0) + (long long)p.PXg * kyf;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int kz = j + q * TPL;
                     const int kzf = kz <= N / 2 ? kz : N - kz;
-                    cp_async_real<T>(sstage + q * SSTRIDE, base + (long long)p.PX * (Lyh + 1) * kzf);
+                    cp_async_real<T>(sstage + q * SSTRIDE, base + (long long)p.PXg * (Lyh + 1) * kzf);
                 }
             }
             cp_async_commit();
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
                 }
                 if constexpr (KIND == GREEN_CATHODE) {
                     const int kzf = kz <= N / 2 ? kz : N - kz;
-                    C h = __ldg(p.H + c * p.H_scomp + kx + (long long)p.PX * (kyf + (long long)(Lyh + 1) * kzf));
+                    C h = __ldg(p.H + c * p.H_scomp + (kx + p.kx0) + (long long)p.PXg * (kyf + (long long)(Lyh + 1) * kzf));
                     const T py = (c == 1) ? (T)-1 : (T)1, pxy = (c == 0 || c == 1) ? (T)-1 : (T)1;
                     if (ky > Lyh) h = cscale(h, py);
                     if (kz > N / 2) h = cmake<C>(pxy * h.x, -pxy * h.y);
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(tz_for(N) * (N / 8), z_minblocks<T>()) k_z_fus
                     acc = cadd(acc, cmul(m, h));
                 }
                 if constexpr (KIND == GREEN_FULL) {
-                    const C g = ld_stream(p.H + c * p.H_scomp + kx + (long long)p.PX * (ky + (long long)p.Lyg * kz));
+                    const C g = ld_stream(p.H + c * p.H_scomp + (kx + p.kx0) + (long long)p.PXg * (ky + (long long)p.Lyg * kz));
                     acc = cmul(spec[q], g);
                 }
             }
@@ -374,8 +384,8 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
     auto load_S = [&](int c) {   // leader only
         unsigned long long* bar = bars + 1 + (c & 1);
         mbar_expect_tx(bar, s_bytes);
-        tma_load_4d(sbuf(c & 1), &mapS, kx0, kyf, 0, c, bar);
-        tma_load_4d(sbuf(c & 1) + SR * TX, &mapS, kx0, kyf, SR, c, bar);
+        tma_load_4d(sbuf(c & 1), &mapS, kx0 + p.kx0, kyf, 0, c, bar);
+        tma_load_4d(sbuf(c & 1) + SR * TX, &mapS, kx0 + p.kx0, kyf, SR, c, bar);
     };
 
     if (leader) {
@@ -595,7 +605,7 @@ k_z_eo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtenso
     const unsigned s_bytes = (unsigned)PZ * sizeof(T);
 
     auto load_S = [&](int c) {   // lane 0 of a valid warp
-        const T* src = p.St + (((long long)c * p.ninner + kx) * (Lyh + 1) + kyf) * PZ;
+        const T* src = p.St + (((long long)c * p.ninner_g + kx + p.kx0) * (Lyh + 1) + kyf) * PZ;
         mbar_expect_tx(sbar + (c & 1), s_bytes);
         bulk_load_1d(sbuf + (c & 1) * PZ, src, s_bytes, sbar + (c & 1));
     };
@@ -744,6 +754,13 @@ struct XParams {
     // generator variant only: the generated lines are even (odd) about index 0, so their spectrum is purely real
     // (imaginary); real_out = 1 (2) stores just that part as a REAL line of pitch PX (columns ninner..PX-1 zeroed)
     int real_out;
+    // kx-slab solve (multi-GPU): the complex line is cut into blocks of `split` bins, one per rank.
+    //   k_x_r2c: bin k of line l is stored through out_peer[k / split] at (l + line0) * split + k % split (the pitch on the
+    //            receiving side is `split`; line0 = this rank's first global line), + component * cplx_scomp
+    //   k_x_c2r: bin k of line l is read from in + (k / split) * sblock + l * split + k % split
+    int split;
+    long long line0, sblock;
+    void* out_peer[SCB_MAX_RANKS];
 };
 
 template <typename T, int N, bool GEN>
@@ -823,6 +840,27 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
             return;
         }
     }
+    if (p.split) {   // kx-slab solve: every bin goes to the rank that owns its kx block
+        const long long coff = (long long)blockIdx.y * p.cplx_scomp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = j + q * TPL;
+            const C zk = v[q];
+            const C zm = lay.ld((N - k) & (N - 1));
+            const C A = cmake<C>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+            const C B = cmake<C>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
+            C* dst = static_cast<C*>(p.out_peer[k / p.split]) + coff + (k % p.split);
+            if (va) dst[(la + p.line0) * p.split] = A;
+            if (vb) dst[(lb + p.line0) * p.split] = B;
+        }
+        if (j == 0) {
+            const int k = N / 2;
+            C* dst = static_cast<C*>(p.out_peer[k / p.split]) + coff + (k % p.split);
+            if (va) dst[(la + p.line0) * p.split] = cmake<C>(v[4].x, 0);
+            if (vb) dst[(lb + p.line0) * p.split] = cmake<C>(v[4].y, 0);
+        }
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int k = j + q * TPL;
@@ -850,15 +888,18 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> 
     const long long la = 2 * pair, lb = 2 * pair + 1;
     const bool va = la < p.nlines, vb = lb < p.nlines;
     LayoutLine<C> lay(reinterpret_cast<C*>(smem_raw) + (size_t)lp * ROW);
-    const C* ia = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + la * p.PX;
-    const C* ib = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + lb * p.PX;
+    // kx-slab solve: bin k sits in block k / split (one block per source rank), pitch `split` inside the block
+    const long long lpitch = p.split ? p.split : p.PX;
+    const C* ia = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + la * lpitch;
+    const C* ib = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + lb * lpitch;
+    auto bin = [&](int k) -> long long { return p.split ? (long long)(k / p.split) * p.sblock + (k % p.split) : (long long)k; };
 
     // Z[k] = A[k] + i B[k],  Z[N-k] = conj(A[k]) + i conj(B[k])
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int k = j + q * TPL;
-        const C a = va ? ld_stream(ia + k) : cmake<C>(0, 0);
-        const C b = vb ? ld_stream(ib + k) : cmake<C>(0, 0);
+        const C a = va ? ld_stream(ia + bin(k)) : cmake<C>(0, 0);
+        const C b = vb ? ld_stream(ib + bin(k)) : cmake<C>(0, 0);
         if (k == 0) {
             lay.st(0, cmake<C>(a.x, b.x));
         } else {
@@ -867,8 +908,8 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> 
         }
     }
     if (j == 0) {
-        const C a = va ? ld_stream(ia + N / 2) : cmake<C>(0, 0);
-        const C b = vb ? ld_stream(ib + N / 2) : cmake<C>(0, 0);
+        const C a = va ? ld_stream(ia + bin(N / 2)) : cmake<C>(0, 0);
+        const C b = vb ? ld_stream(ib + bin(N / 2)) : cmake<C>(0, 0);
         lay.st(N / 2, cmake<C>(a.x, b.x));
     }
     __syncthreads();

@@ -32,8 +32,18 @@ template <> cudaError_t launch_lines<SCB_T>(int N, int dir, const LinesParams<SC
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <> cudaError_t launch_z_fused<SCB_T>(int N, int kind, const ZParams<SCB_T>& p, cudaStream_t s) {
+// callers that do not use the kx-slab decomposition leave the spectrum-side extents at zero: same as the data's
+static ZParams<SCB_T> with_spectrum_extents(ZParams<SCB_T> p) {
+    if (p.PXg == 0) {
+        p.PXg = p.PX;
+        p.ninner_g = p.ninner;
+    }
+    return p;
+}
+
+template <> cudaError_t launch_z_fused<SCB_T>(int N, int kind, const ZParams<SCB_T>& p0, cudaStream_t s) {
     using C = cx_t<SCB_T>;
+    const ZParams<SCB_T> p = with_spectrum_extents(p0);
     cudaError_t e = cudaErrorInvalidValue;
 #define X(NN)                                                                                     \
     if (N == NN) {                                                                                \
@@ -57,8 +67,9 @@ template <> cudaError_t launch_z_fused<SCB_T>(int N, int kind, const ZParams<SCB
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC,
+template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p0, const CUtensorMap& mapB, const CUtensorMap& mapC,
                                              const CUtensorMap& mapS, cudaStream_t s) {
+    const ZParams<SCB_T> p = with_spectrum_extents(p0);
     cudaError_t e = cudaErrorNotSupported;
 #define X(NN)                                                                                     \
     if (N == NN) {                                                                                \
@@ -72,8 +83,9 @@ template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p, cons
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <> cudaError_t launch_z_eo<SCB_T>(const ZParams<SCB_T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s) {
+template <> cudaError_t launch_z_eo<SCB_T>(const ZParams<SCB_T>& p0, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s) {
     using LY = ZEoLayout<SCB_T>;
+    const ZParams<SCB_T> p = with_spectrum_extents(p0);
     dim3 grid((p.ninner + LY::TX - 1) / LY::TX, p.Ly), block(32 * LY::TX);
     cudaError_t e = set_smem(k_z_eo<SCB_T>, LY::BYTES);
     if (e == cudaSuccess) k_z_eo<SCB_T><<<grid, block, LY::BYTES, s>>>(mapB, mapC, p);
