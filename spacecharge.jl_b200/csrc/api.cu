@@ -774,7 +774,11 @@ int launch_z_pass(scb_handle* h, const Plan& pl, ZParams<T>& p, int mode, const 
             return SCB_OK;
         }
     }
-    if (mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512) {
+    // (kx-slab solve: the spectrum tile of k_z_tma starts at this rank's global kx0; a start that is not 16-byte aligned
+    // made the bulk tensor load trap -- illegal instruction on the odd ranks of a 4-rank Float32 run -- so those ranks
+    // take k_z_fused)
+    if (mode == 0 && z_tma_enabled() && pl.n[2] <= 256 && pl.L[2] >= 16 && pl.L[2] <= 512 &&
+        ((size_t)p.kx0 * sizeof(T)) % 16 == 0) {
         // all global traffic of the pass through the TMA unit (see k_z_tma)
         const cuuint32_t TX = (cuuint32_t)tz_for(pl.L[2]);
         const cuuint64_t PXg = pl.PX, Lyh1 = pl.L[1] / 2 + 1, Lzh1 = pl.L[2] / 2 + 1;
