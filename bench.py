@@ -126,10 +126,15 @@ def cpu_reference_run(npart, grid, at_cathode, zshift, steps, warmup, budget_s=1
     """The reference's CPU structure on the host cores.  One step = the full-grid solve plus deposit/interpolate on a
     bounded particle sample; the particle passes are then measured ONCE on all particles, and `value` uses that
     measurement (no extrapolation) next to the mean solve time."""
+    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 into every rank.  The C port sets its OpenMP thread count explicitly, but
+    # scipy's pocketfft also slows down 3x under that variable even with workers=cores (measured: 0.20 -> 0.65 s for a
+    # 256^3 C2C), so the variable is overridden BEFORE scipy is first imported (this function is its only importer here)
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(cores)
     from oracle import spacecharge_oracle as so
     from oracle.cpu_reference import RefPort
 
-    cores = os.cpu_count() or 1
     t_begin = time.perf_counter()
     nsample = min(npart, 4_000_000)
     rng = np.random.default_rng(42)
