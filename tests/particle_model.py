@@ -100,3 +100,118 @@ def gather_packed_f32(records, lo, delta, x, y, z):
                     acc = term if acc is None else acc + term
         out.append(acc.astype(x.dtype))
     return tuple(out)
+
+
+# ---- cell-ordered regime (csrc/sorted.cu) -----------------------------------------------------------------------------
+def cell_keys(grid, lo, delta, x, y, z, T=np.float64):
+    """k_cell_keys: linear index of the (clamped) cell, ix + nx*(iy + ny*iz)"""
+    nx, ny, nz = grid
+    W = np.promote_types(x.dtype, T)
+    ix, _ = locate(x.astype(W), W.type(lo[0]), W.type(delta[0]), nx)
+    iy, _ = locate(y.astype(W), W.type(lo[1]), W.type(delta[1]), ny)
+    iz, _ = locate(z.astype(W), W.type(lo[2]), W.type(delta[2]), nz)
+    return (ix + nx * (iy + ny * iz)).astype(np.uint32)
+
+
+def radix_sort_pairs(keys, key_bits, tile=4096, warp_keys=256):
+    """launch_sort_pairs: LSD passes of ceil(bits / passes) bits; inside a tile every warp ranks its `warp_keys`
+    consecutive keys in rounds of 32 (rank = keys of the same digit in earlier rounds / lower lanes), the warps' counts
+    are prefix-summed per digit, and the tile's digits start at the exclusive scan of the digit-major histogram table.
+    Returns the permutation (index of the key that comes i-th)."""
+    n = len(keys)
+    passes = max(1, (max(key_bits, 1) + 7) // 8)
+    bits = (max(key_bits, 1) + passes - 1) // passes
+    mask = (1 << bits) - 1
+    ntiles = (n + tile - 1) // tile
+    cur_k = keys.astype(np.uint32).copy()
+    cur_v = np.arange(n, dtype=np.uint32)
+    for p in range(passes):
+        shift = p * bits
+        digit = (cur_k >> np.uint32(shift)) & np.uint32(mask)
+        hist = np.zeros((mask + 1, ntiles), dtype=np.int64)                  # digit-major table of k_radix_hist
+        for t in range(ntiles):
+            hist[:, t] = np.bincount(digit[t * tile:(t + 1) * tile], minlength=mask + 1)
+        offs = (np.cumsum(hist.reshape(-1)) - hist.reshape(-1)).reshape(hist.shape)   # ONE exclusive scan
+        out_k, out_v = np.empty_like(cur_k), np.empty_like(cur_v)
+        for t in range(ntiles):
+            d = digit[t * tile:(t + 1) * tile]
+            m = len(d)
+            nwarps = (m + warp_keys - 1) // warp_keys
+            whist = np.zeros((nwarps, mask + 1), dtype=np.int64)
+            rank = np.zeros(m, dtype=np.int64)
+            for w in range(nwarps):
+                seg = d[w * warp_keys:(w + 1) * warp_keys]
+                for r0 in range(0, len(seg), 32):                             # one round: __match_any_sync groups
+                    rnd = seg[r0:r0 + 32]
+                    for lane, dv in enumerate(rnd):
+                        lower = int(np.sum(rnd[:lane] == dv))
+                        rank[w * warp_keys + r0 + lane] = whist[w, dv] + lower
+                    for dv, c in zip(*np.unique(rnd, return_counts=True)):
+                        whist[w, dv] += c                                     # the leader's returning atomicAdd
+            wbase = np.cumsum(whist, axis=0) - whist                          # exclusive prefix over the warps
+            warp_of = np.arange(m) // warp_keys
+            pos = offs[d, t] + wbase[warp_of, d] + rank
+            out_k[pos] = cur_k[t * tile:(t + 1) * tile]
+            out_v[pos] = cur_v[t * tile:(t + 1) * tile]
+        cur_k, cur_v = out_k, out_v
+    return cur_v
+
+
+def deposit_runs(grid, lo, delta, x, y, z, q, T=np.float64, per_lane=8):
+    """k_deposit_runs: every lane walks `per_lane` consecutive particles keeping the corner sums of its current cell; an
+    interloper (differs from the run, next particle back in it) is flushed on its own; the warp's open runs are combined
+    by a segmented scan over adjacent lanes with equal cells and the last lane of each segment flushes.  Returns
+    (rho, flushes): the grid and the number of 8-value flushes that reached memory."""
+    nx, ny, nz = grid
+    W = np.promote_types(x.dtype, T)
+    ix, fx = locate(x.astype(W), W.type(lo[0]), W.type(delta[0]), nx)
+    iy, fy = locate(y.astype(W), W.type(lo[1]), W.type(delta[1]), ny)
+    iz, fz = locate(z.astype(W), W.type(lo[2]), W.type(delta[2]), nz)
+    one = W.type(1)
+    qq = q.astype(W)
+    qx = (qq * (one - fx), qq * fx)
+    wy, wz = (one - fy, fy), (one - fz, fz)
+    vals = np.stack([(qx[a] * wy[b]) * wz[c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], axis=1)   # ((q*wx)*wy)*wz
+    cell = ix + nx * (iy + ny * iz)
+    rho = np.zeros(nx * ny * nz, dtype=T)
+    corner = np.array([a + nx * (b + ny * c) for c in (0, 1) for b in (0, 1) for a in (0, 1)])
+    flushes = 0
+
+    def flush(c, s):
+        nonlocal flushes
+        flushes += 1
+        for k in range(8):
+            rho[c + corner[k]] += T(s[k])
+
+    n = len(x)
+    for wbase in range(0, n, 32 * per_lane):
+        cur = np.full(32, -1, dtype=np.int64)
+        sums = np.zeros((32, 8), dtype=W)
+        for lane in range(32):
+            i0 = wbase + lane * per_lane
+            cnt = min(per_lane, max(0, n - i0))
+            for j in range(cnt):
+                c = cell[i0 + j]
+                nxt = cell[i0 + j + 1] if j + 1 < cnt else -2
+                if c != cur[lane] and cur[lane] >= 0 and nxt == cur[lane]:
+                    flush(c, vals[i0 + j])
+                else:
+                    if c != cur[lane] and cur[lane] >= 0:
+                        flush(cur[lane], sums[lane])
+                    sums[lane] = vals[i0 + j] if c != cur[lane] else sums[lane] + vals[i0 + j]
+                    cur[lane] = c
+        # segmented inclusive scan over the lanes (Hillis-Steele, 5 steps), tails flush
+        start = np.zeros(32, dtype=np.int64)
+        for lane in range(32):
+            start[lane] = lane if lane == 0 or cur[lane] != cur[lane - 1] else start[lane - 1]
+        o = 1
+        while o < 32:
+            prev = sums.copy()
+            for lane in range(32):
+                if lane - o >= start[lane]:
+                    sums[lane] = prev[lane] + prev[lane - o]
+            o <<= 1
+        for lane in range(32):
+            if cur[lane] >= 0 and (lane == 31 or cur[lane + 1] != cur[lane]):
+                flush(cur[lane], sums[lane])
+    return rho.reshape(nz, ny, nx).transpose(2, 1, 0), flushes
