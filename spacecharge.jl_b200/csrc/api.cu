@@ -1010,6 +1010,7 @@ Geom3 make_geom(const int64_t n[3], const double lo[3], const double delta[3]) {
         g.lo[a] = lo[a];
         g.delta[a] = delta[a];
         g.rinv[a] = 1.0 / delta[a];
+        g.rinvf[a] = 1.0f / (float)delta[a];
     }
     return g;
 }

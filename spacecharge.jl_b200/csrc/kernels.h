@@ -21,6 +21,7 @@ struct Geom3 {
     double lo[3];
     double delta[3];
     double rinv[3];   // RN(1 / delta), formed on the host (div_exact in particle_common.cuh)
+    float rinvf[3];   // RN_f32(1 / (float)delta) for the all-Float32 kernels
     int n[3];
     int l2_keep = 1;   // 1: grid-side accesses of the particle passes carry an L2 evict_last policy (SCB_L2_HINT=0 disables)
     // gather kernels only: handle the particles whose z cell lies in [zlo, zhi) but not in [exlo, exhi) -- the

@@ -52,7 +52,19 @@ __device__ __forceinline__ double div_exact(double a, double d, double rinv) {
     const double e1 = __fma_rn(-q1, d, a);
     return __fma_rn(e1, rinv, q1);
 }
-__device__ __forceinline__ float div_exact(float a, float d, float) { return __fdiv_rn(a, d); }
+// the same steps in Float32 (y = RN_f32(1 / d) formed in Float32 on the host: Geom3::rinvf)
+__device__ __forceinline__ float div_exact(float a, float d, float rinv) {
+    const float q0 = a * rinv;
+    const float e0 = __fmaf_rn(-q0, d, a);
+    const float q1 = __fmaf_rn(e0, rinv, q0);
+    const float e1 = __fmaf_rn(-q1, d, a);
+    return __fmaf_rn(e1, rinv, q1);
+}
+
+// RN(1 / delta) in the working precision (a double-rounded Float32 reciprocal would not satisfy Markstein's condition)
+template <typename W> __device__ __forceinline__ W geom_rinv(const Geom3& g, int a);
+template <> __device__ __forceinline__ double geom_rinv<double>(const Geom3& g, int a) { return g.rinv[a]; }
+template <> __device__ __forceinline__ float geom_rinv<float>(const Geom3& g, int a) { return g.rinvf[a]; }
 
 __device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
 __device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
@@ -61,7 +73,7 @@ __device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t);
 // the floor taken by the float -> int conversion (saturating, so the integer clamp equals the clamp of the float value)
 template <typename W>
 __device__ __forceinline__ void locate_axis(W p, const Geom3& g, int a, int& i, W& f) {
-    const W t = div_exact(p - (W)g.lo[a], (W)g.delta[a], (W)g.rinv[a]);
+    const W t = div_exact(p - (W)g.lo[a], (W)g.delta[a], geom_rinv<W>(g, a));
     i = min(max(floor_to_int(t), 0), g.n[a] - 2);
     f = t - (W)i;
 }

@@ -538,9 +538,9 @@ __global__ void k_cell_index(long long np, const P* __restrict__ x, const P* __r
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
     // the product kernels' quotient (div_exact), floor unclamped
-    ix[i] = (long long)floor(div_exact((W)x[i] - (W)g.lo[0], (W)g.delta[0], (W)g.rinv[0]));
-    iy[i] = (long long)floor(div_exact((W)y[i] - (W)g.lo[1], (W)g.delta[1], (W)g.rinv[1]));
-    iz[i] = (long long)floor(div_exact((W)z[i] - (W)g.lo[2], (W)g.delta[2], (W)g.rinv[2]));
+    ix[i] = (long long)floor(div_exact((W)x[i] - (W)g.lo[0], (W)g.delta[0], geom_rinv<W>(g, 0)));
+    iy[i] = (long long)floor(div_exact((W)y[i] - (W)g.lo[1], (W)g.delta[1], geom_rinv<W>(g, 1)));
+    iz[i] = (long long)floor(div_exact((W)z[i] - (W)g.lo[2], (W)g.delta[2], geom_rinv<W>(g, 2)));
 }
 
 // ---- extrema -------------------------------------------------------------------------------

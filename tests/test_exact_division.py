@@ -61,3 +61,44 @@ def test_special_spacings():
         check(0.0, d)
         check(d, d)
         check(255 * d, d)
+
+
+# ---- the same sequence in Float32 (all-Float32 kernels: Float32 particles on a Float32 mesh) --------------------------
+def f32(v):
+    return np.float32(v)
+
+
+def fma32(x, y, z):
+    return f32(float(Fraction(float(x)) * Fraction(float(y)) + Fraction(float(z))))   # exact, then ONE rounding to Float32
+
+
+def div_exact32(a, d):
+    rinv = f32(1.0) / d
+    q0 = a * rinv
+    e0 = fma32(-q0, d, a)
+    q1 = fma32(e0, rinv, q0)
+    e1 = fma32(-q1, d, a)
+    return fma32(e1, rinv, q1)
+
+
+def check32(a, d):
+    a, d = f32(a), f32(d)
+    want = f32(float(Fraction(float(a)) / Fraction(float(d))))
+    assert want == a / d
+    got = div_exact32(a, d)
+    assert got == want, (float(a).hex(), float(d).hex(), float(got).hex(), float(want).hex())
+
+
+def test_float32_sequence():
+    rng = np.random.default_rng(4)
+    for _ in range(4000):
+        d = f32((0.5 + rng.random()) * 10.0 ** rng.integers(-7, -1))
+        check32(f32(rng.random() * 10.0 ** rng.integers(-8, 0)), d)
+        k = int(rng.integers(0, 1024))
+        a = f32(k) * d
+        check32(a, d)
+        check32(np.nextafter(a, f32(np.inf)), d)
+        check32(np.nextafter(a, f32(-np.inf)), d)
+    for d in (f32(float.fromhex("0x1.fffffep-14")), f32(2.0 ** -20), f32(1e-6)):
+        for a in rng.random(300).astype(np.float32) * f32(300) * d:
+            check32(a, d)
