@@ -831,12 +831,10 @@ cudaError_t launch_sort_pairs(void* scratch, long long n, int key_bits, unsigned
     if (key_bits < 1) key_bits = 1;
     const int passes = (key_bits + 7) / 8;
     const int bits = sort_digit_bits(key_bits);
-    static bool attr_set = false;
     const size_t smem = (size_t)(2 * SORT_TILE + SORT_WARPS * 256 + 512) * 4;
-    if (!attr_set) {
+    {   // per call: the attribute belongs to the current device, and a process may drive several
         cudaError_t e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     // value buffers alternate so that the LAST pass writes perm_out
     unsigned* vbuf[2];
