@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const unsigned* __r
     if (tid < 256) sh[tid] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * SORT_TILE + warp * (SORT_KPT * 32) + lane;
-    // all 16 keys first (independent loads), then the counting: one vote per round catches the case that bounds shared
+    // all of the thread's keys first (independent loads), then the counting: one vote per round catches the case that bounds shared
     // atomics (every lane on the same counter -- the last pass of an almost ordered bunch), everything else goes through
     // native integer atomics (the match-based count of the first version made this kernel latency-bound: 0.60 ms for
     // 0.4 GB)
