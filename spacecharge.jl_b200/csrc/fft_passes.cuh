@@ -763,7 +763,8 @@ struct XParams {
     void* out_peer[SCB_MAX_RANKS];
 };
 
-template <typename T, int N, bool GEN>
+// SPLIT: kx-slab solve (multi-GPU), a compile-time switch so that the single-GPU instantiation carries none of it
+template <typename T, int N, bool GEN, bool SPLIT = false>
 __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> p) {
     using C = cx_t<T>;
     constexpr int TPL = N / 8;
@@ -840,7 +841,7 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
             return;
         }
     }
-    if (p.split) {   // kx-slab solve: every bin goes to the rank that owns its kx block
+    if constexpr (SPLIT) {   // kx-slab solve: every bin goes to the rank that owns its kx block
         const long long coff = (long long)blockIdx.y * p.cplx_scomp;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -877,7 +878,7 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
     }
 }
 
-template <typename T, int N>
+template <typename T, int N, bool SPLIT = false>
 __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> p) {
     using C = cx_t<T>;
     constexpr int TPL = N / 8;
@@ -889,10 +890,10 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_c2r(const XParams<T> 
     const bool va = la < p.nlines, vb = lb < p.nlines;
     LayoutLine<C> lay(reinterpret_cast<C*>(smem_raw) + (size_t)lp * ROW);
     // kx-slab solve: bin k sits in block k / split (one block per source rank), pitch `split` inside the block
-    const long long lpitch = p.split ? p.split : p.PX;
+    const long long lpitch = SPLIT ? p.split : p.PX;
     const C* ia = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + la * lpitch;
     const C* ib = static_cast<const C*>(p.in) + (long long)blockIdx.y * p.cplx_scomp + lb * lpitch;
-    auto bin = [&](int k) -> long long { return p.split ? (long long)(k / p.split) * p.sblock + (k % p.split) : (long long)k; };
+    auto bin = [&](int k) -> long long { return SPLIT ? (long long)(k / p.split) * p.sblock + (k % p.split) : (long long)k; };
 
     // Z[k] = A[k] + i B[k],  Z[N-k] = conj(A[k]) + i conj(B[k])
 #pragma unroll

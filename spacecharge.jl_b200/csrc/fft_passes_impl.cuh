@@ -104,6 +104,9 @@ template <> cudaError_t launch_x_r2c<SCB_T>(int N, const XParams<SCB_T>& p, int 
         if (sizeof(SCB_T) == 8 && p.gen.D) {                                                      \
             e = set_smem(k_x_r2c<SCB_T, NN, sizeof(SCB_T) == 8>, sm);                             \
             if (e == cudaSuccess) k_x_r2c<SCB_T, NN, sizeof(SCB_T) == 8><<<grid, block, sm, s>>>(p); \
+        } else if (p.split) {                                                                     \
+            e = set_smem(k_x_r2c<SCB_T, NN, false, true>, sm);                                    \
+            if (e == cudaSuccess) k_x_r2c<SCB_T, NN, false, true><<<grid, block, sm, s>>>(p);     \
         } else {                                                                                  \
             e = set_smem(k_x_r2c<SCB_T, NN, false>, sm);                                          \
             if (e == cudaSuccess) k_x_r2c<SCB_T, NN, false><<<grid, block, sm, s>>>(p);           \
@@ -123,8 +126,13 @@ template <> cudaError_t launch_x_c2r<SCB_T>(int N, const XParams<SCB_T>& p, int 
         const size_t sm = (size_t)LP * LayoutLine<C>::row(NN) * sizeof(C);                        \
         const long long pairs = (p.nlines + 1) / 2;                                               \
         dim3 grid((unsigned)((pairs + LP - 1) / LP), ncomp), block(NN / 8, LP);                   \
-        e = set_smem(k_x_c2r<SCB_T, NN>, sm);                                                     \
-        if (e == cudaSuccess) k_x_c2r<SCB_T, NN><<<grid, block, sm, s>>>(p);                      \
+        if (p.split) {                                                                            \
+            e = set_smem(k_x_c2r<SCB_T, NN, true>, sm);                                           \
+            if (e == cudaSuccess) k_x_c2r<SCB_T, NN, true><<<grid, block, sm, s>>>(p);            \
+        } else {                                                                                  \
+            e = set_smem(k_x_c2r<SCB_T, NN>, sm);                                                 \
+            if (e == cudaSuccess) k_x_c2r<SCB_T, NN><<<grid, block, sm, s>>>(p);                  \
+        }                                                                                         \
     }
     SCB_FOR_EACH_N(X)
 #undef X
