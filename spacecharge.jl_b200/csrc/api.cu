@@ -448,7 +448,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
     ent.ncomp = ncomp;
     ent.t_off = 0;
     ent.PZ = 0;
-    if (key.kind == 0 && z_eo_eligible(pl)) {
+    if ((key.kind == 0 || key.kind == 1) && z_eo_eligible(pl)) {   // kz'-fastest copy for the even/odd-bin z pass
         ent.PZ = (Lzh1 + 7) / 8 * 8;
         ent.t_off = al(ent.bytes);
         ent.bytes = ent.t_off + (size_t)ncomp * pl.ninner * Lyh1 * ent.PZ * elem;
@@ -600,7 +600,7 @@ int build_green(scb_handle* h, const Plan& pl, const GreenKey& key, GreenEntry& 
         for (int c = 0; c < ncomp; ++c) {
             const char* src = static_cast<const char*>(ent.data) + (size_t)c * per_comp * elem;
             char* dstT = static_cast<char*>(ent.data) + ent.t_off + (size_t)c * pl.ninner * Lyh1 * ent.PZ * elem;
-            SCB_CUDA(h, launch_green_transpose(dstT, src, f64, pl.ninner, pl.PX, Lyh1, Lzh1, ent.PZ, h->stream));
+            SCB_CUDA(h, launch_green_transpose(dstT, src, f64, pl.ninner, pl.PX, Lyh1, Lzh1, ent.PZ, h->stream, key.kind == 1));
         }
         h->launches += ncomp;
     }
@@ -751,12 +751,13 @@ int ensure_chunk_streams(scb_handle* h) {
 // kernel when it applies (free space, padded z length 512), else the TMA kernel (free space, nz <= 256), else k_z_fused
 // (cathode image, general offset, long z).  `p` arrives with everything but the tensor maps' business filled in.
 template <typename T>
-int launch_z_pass(scb_handle* h, const Plan& pl, ZParams<T>& p, int mode, const GreenEntry* gfree, const cx_t<T>* B,
-                  cx_t<T>* Cc, size_t comp_stride, int nc) {
+int launch_z_pass(scb_handle* h, const Plan& pl, ZParams<T>& p, int mode, const GreenEntry* gfree, const GreenEntry* gaux,
+                  const cx_t<T>* B, cx_t<T>* Cc, size_t comp_stride, int nc) {
     const int kind = mode == 0 ? GREEN_FREE : mode == 1 ? GREEN_CATHODE : GREEN_FULL;
     const bool f64 = sizeof(T) == 8;
     const cuuint64_t s = sizeof(T), PX = p.PX, L1 = pl.L[1], nz = pl.n[2];
-    if (mode == 0 && z_eo_enabled() && z_eo_eligible(pl) && gfree->t_off && gfree->PZ == ZEoLayout<T>::PZ) {
+    const bool eo_free = mode == 0, eo_cath = mode == 1 && gaux && gaux->t_off && gaux->PZ == ZEoLayout<T>::PZ;
+    if ((eo_free || eo_cath) && z_eo_enabled() && z_eo_eligible(pl) && gfree->t_off && gfree->PZ == ZEoLayout<T>::PZ) {
         // even/odd-bin variant: one warp per line, 256-point transforms with a single exchange (see k_z_eo)
         const cuuint32_t TX = ZEoLayout<T>::TX;
         const int rowb = ZEoLayout<T>::ROWB;
@@ -770,7 +771,8 @@ int launch_z_pass(scb_handle* h, const Plan& pl, ZParams<T>& p, int mode, const 
         if (make_tensor_map(&mB, f64, 3, B, dB, sB, bB, swz) && make_tensor_map(&mC, f64, 4, Cc, dC, sC, bC, swz)) {
             p.St = reinterpret_cast<const T*>(static_cast<const char*>(gfree->data) + gfree->t_off);
             p.PZ = gfree->PZ;
-            SCB_CUDA(h, launch_z_eo<T>(p, mB, mC, h->stream));
+            if (eo_cath) p.Ht = reinterpret_cast<const cx_t<T>*>(static_cast<const char*>(gaux->data) + gaux->t_off);
+            SCB_CUDA(h, launch_z_eo<T>(p, mB, mC, h->stream, eo_cath));
             return SCB_OK;
         }
     }
@@ -893,7 +895,7 @@ int run_solve(scb_handle* h, const T* rho, T* efield, const Plan& pl, const doub
             p.H = static_cast<const C*>(gaux->data);
             p.H_scomp = gaux->scomp;
         }
-        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, B, Cc, szB, nc));
+        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, gaux, B, Cc, szB, nc));
     }
     tick(h, 11);
     // B2 + B3.  Plain form: B2 writes the y-pruned intermediate D (3A bytes) to HBM and B3 reads it back.  Chunked form
@@ -1891,7 +1893,7 @@ int run_solve_sharded_kx(scb_handle* h, const T* rho_partial, T* efield, const P
         p.kx0 = kx0; p.ninner_g = pl.ninner; p.PXg = pl.PX;
         p.S = static_cast<const T*>(gfree->data); p.S_scomp = gfree->scomp;
         if (gaux) { p.H = static_cast<const C*>(gaux->data); p.H_scomp = gaux->scomp; }
-        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, B1, C1, b1, 3));
+        SCB_TRY(launch_z_pass<T>(h, pl, p, mode, gfree, gaux, B1, C1, b1, 3));
     }
     tick(h, 11);
     if (ninl > 0) {  // B2, local; plane z goes to the owner of its z slab, into the block reserved for this rank

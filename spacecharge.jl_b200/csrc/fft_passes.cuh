@@ -164,8 +164,10 @@ struct ZParams {
     // GREEN_FULL: G_c, complex, unfolded [kx + PX*(ky + Ly*kz)]
     const cx_t<T>* H;
     long long H_scomp;
-    // k_z_eo: copy of S with kz' fastest, St[((c*ninner + kx)*(Ly/2+1) + ky')*PZ + kz']
+    // k_z_eo: copy of S with kz' fastest, St[((c*ninner + kx)*(Ly/2+1) + ky')*PZ + kz']; cathode: the image spectrum
+    // H in the same arrangement (complex entries)
     const T* St;
+    const cx_t<T>* Ht;
     int PZ;
 };
 
@@ -577,7 +579,12 @@ struct ZEoLayout {
 // Three tile buffers: [0] receives the input and, once every warp has taken its line out of it, serves as output
 // staging for component 2; components 0 and 1 are staged in [1] and [2] -- so no component waits for the bulk store of
 // the previous one to drain its buffer (a potential as fourth component reuses [1] after the first store has read it).
-template <typename T>
+// CATH: the cathode image term is added in the spectral multiply, acc += R(kx, ky, -kz) * H(kx, ky, kz) (DESIGN.md
+// section 3, identity (ii)).  The mirrored forward bin N - b of lane (h, t), register k2 sits in register 15 - k2 of
+// lane (h, t') with t' = 15 - t (odd bins) or 16 - t (even bins, t > 0), and in the lane's own register (16 - k2) % 16
+// for the even bins of t = 0: one shuffle per value, nothing parked in shared memory.  H comes from its kz'-fastest
+// copy straight from global memory: for a fixed k2 the 32 lanes read 32 consecutive entries (512 bytes).
+template <typename T, bool CATH>
 __global__ void __launch_bounds__(32 * SCB_ZEO_TX, zeo_minblocks<T>())
 k_z_eo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC, const ZParams<T> p) {
     using C = cx_t<T>;
@@ -624,6 +631,17 @@ k_z_eo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtenso
         load_S(0);
         if (p.ncomp > 1) load_S(1);
     }
+    if constexpr (CATH) {
+        // the image-spectrum rows of this line (one 4 KB row per component) are read straight from global memory inside
+        // the component loop: ask the L2 for them now, while the input tile travels and the forward transform runs
+        if (valid) {
+            for (int c = 0; c < p.ncomp; ++c) {
+                const char* row = reinterpret_cast<const char*>(p.Ht + (((long long)c * p.ninner_g + kx + p.kx0) * (Lyh + 1) + kyf) * PZ);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128 * lane));
+                if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128 * 32));
+            }
+        }
+    }
     // per-thread roots (table: exp(-2 pi i k / 512)): w256^t, w512^t (odd half), w512^(2t+h)
     const C bf = __ldg(p.tw + 2 * t);
     const C cf = h ? __ldg(p.tw + t) : cmake<C>(1, 0);
@@ -662,6 +680,19 @@ k_z_eo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtenso
                 if ((c == 1 && ky > Lyh) || (c == 2 && b > N / 2)) s = -s;
                 // field: (a + ib) * (i s) = s * (-b + i a);  potential: (a + ib) * s
                 wv[k2] = c == 3 ? cmake<C>(spec[k2].x * s, spec[k2].y * s) : cmake<C>(-spec[k2].y * s, spec[k2].x * s);
+                if constexpr (CATH) {
+                    C hv = __ldg(p.Ht + (((long long)c * p.ninner_g + kx + p.kx0) * (Lyh + 1) + kyf) * PZ + kzf);
+                    // folding rules of the image spectrum: H(Ly - ky) = p_y H(ky), H(Lz - kz) = p_x p_y conj(H(kz))
+                    const T py = (c == 1) ? (T)-1 : (T)1, pxy = (c == 0 || c == 1) ? (T)-1 : (T)1;
+                    if (ky > Lyh) hv = cscale(hv, py);
+                    if (b > N / 2) hv = cmake<C>(pxy * hv.x, -pxy * hv.y);
+                    const int srcl = h ? 31 - t : ((16 - t) & 15);
+                    C m;
+                    m.x = __shfl_sync(0xffffffffu, spec[15 - k2].x, srcl);
+                    m.y = __shfl_sync(0xffffffffu, spec[15 - k2].y, srcl);
+                    if (lane == 0) m = spec[(16 - k2) & 15];
+                    wv[k2] = cadd(wv[k2], cmul(m, hv));
+                }
             }
             __syncwarp();
             if (lane == 0 && c + 2 < p.ncomp) load_S(c + 2);   // the whole warp is past its reads of this row
@@ -939,7 +970,8 @@ template <typename T> cudaError_t launch_z_fused(int N, int kind, const ZParams<
 template <typename T> cudaError_t launch_z_tma(int N, const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC,
                                                 const CUtensorMap& mapS, cudaStream_t s);
 
-template <typename T> cudaError_t launch_z_eo(const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s);
+template <typename T> cudaError_t launch_z_eo(const ZParams<T>& p, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s,
+                                              bool cathode = false);
 template <typename T> cudaError_t launch_x_r2c(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 template <typename T> cudaError_t launch_x_c2r(int N, const XParams<T>& p, int ncomp, cudaStream_t s);
 bool fft_len_supported(int N);

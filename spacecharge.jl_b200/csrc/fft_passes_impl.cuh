@@ -83,12 +83,19 @@ template <> cudaError_t launch_z_tma<SCB_T>(int N, const ZParams<SCB_T>& p0, con
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <> cudaError_t launch_z_eo<SCB_T>(const ZParams<SCB_T>& p0, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s) {
+template <> cudaError_t launch_z_eo<SCB_T>(const ZParams<SCB_T>& p0, const CUtensorMap& mapB, const CUtensorMap& mapC, cudaStream_t s,
+                                           bool cathode) {
     using LY = ZEoLayout<SCB_T>;
     const ZParams<SCB_T> p = with_spectrum_extents(p0);
     dim3 grid((p.ninner + LY::TX - 1) / LY::TX, p.Ly), block(32 * LY::TX);
-    cudaError_t e = set_smem(k_z_eo<SCB_T>, LY::BYTES);
-    if (e == cudaSuccess) k_z_eo<SCB_T><<<grid, block, LY::BYTES, s>>>(mapB, mapC, p);
+    cudaError_t e;
+    if (cathode) {
+        e = set_smem(k_z_eo<SCB_T, true>, LY::BYTES);
+        if (e == cudaSuccess) k_z_eo<SCB_T, true><<<grid, block, LY::BYTES, s>>>(mapB, mapC, p);
+    } else {
+        e = set_smem(k_z_eo<SCB_T, false>, LY::BYTES);
+        if (e == cudaSuccess) k_z_eo<SCB_T, false><<<grid, block, LY::BYTES, s>>>(mapB, mapC, p);
+    }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

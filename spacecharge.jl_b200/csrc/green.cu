@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_green_transpose(T* __restrict__ St, con
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int kz = kz0 + ty + 8 * r, kx = kx0 + tx;
-        tile[ty + 8 * r][tx] = (kz < Lzh1 && kx < ninner) ? S[kx + (long long)PX * (ky + (long long)Lyh1 * kz)] : (T)0;
+        tile[ty + 8 * r][tx] = (kz < Lzh1 && kx < ninner) ? S[kx + (long long)PX * (ky + (long long)Lyh1 * kz)] : T{};
     }
     __syncthreads();
 #pragma unroll
@@ -165,9 +165,13 @@ cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_green_transpose(void* St, const void* S, int dt_f64, int ninner, int PX, int Lyh1, int Lzh1, int PZ, cudaStream_t s) {
+cudaError_t launch_green_transpose(void* St, const void* S, int dt_f64, int ninner, int PX, int Lyh1, int Lzh1, int PZ, cudaStream_t s,
+                                   int complex_elems) {
     dim3 grid((ninner + 31) / 32, (PZ + 31) / 32, Lyh1);
-    if (dt_f64) k_green_transpose<double><<<grid, 256, 0, s>>>((double*)St, (const double*)S, ninner, PX, Lyh1, Lzh1, PZ);
+    if (complex_elems) {   // image-charge spectrum: complex entries
+        if (dt_f64) k_green_transpose<double2><<<grid, 256, 0, s>>>((double2*)St, (const double2*)S, ninner, PX, Lyh1, Lzh1, PZ);
+        else k_green_transpose<float2><<<grid, 256, 0, s>>>((float2*)St, (const float2*)S, ninner, PX, Lyh1, Lzh1, PZ);
+    } else if (dt_f64) k_green_transpose<double><<<grid, 256, 0, s>>>((double*)St, (const double*)S, ninner, PX, Lyh1, Lzh1, PZ);
     else k_green_transpose<float><<<grid, 256, 0, s>>>((float*)St, (const float*)S, ninner, PX, Lyh1, Lzh1, PZ);
     return cudaGetLastError();
 }

@@ -48,7 +48,9 @@ cudaError_t launch_green_point(double* P, const IgfGeom& g, int icomp, cudaStrea
 cudaError_t launch_green_reference_layout(void* out, int dt_f64, const double* P, int sx, int sy, int sz, cudaStream_t s);
 // D: the differenced values, (cnt-1)^3 doubles
 cudaError_t launch_green_diff(double* D, const double* P, const IgfGeom& g, cudaStream_t s);
-cudaError_t launch_green_transpose(void* St, const void* S, int dt_f64, int ninner, int PX, int Lyh1, int Lzh1, int PZ, cudaStream_t s);
+// complex_elems: the entries are complex (image-charge spectrum) instead of real (free-space S)
+cudaError_t launch_green_transpose(void* St, const void* S, int dt_f64, int ninner, int PX, int Lyh1, int Lzh1, int PZ, cudaStream_t s,
+                                   int complex_elems = 0);
 cudaError_t launch_green_real_to_f32(void* S, const double* spec, long long total, cudaStream_t s);
 cudaError_t launch_green_compress_free(void* S, int dt_f64, const double2* spec, int ninner, int PX, int Lyh1, int Lzh1,
                                        int take_real, cudaStream_t s);

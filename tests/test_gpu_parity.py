@@ -123,7 +123,9 @@ def _solve_pair(scb, oracle, grid, lo, hi, gamma, rho, at_cathode, T=np.float64)
     return mesh, ref
 
 
-@pytest.mark.parametrize("grid", [(8, 8, 8), (16, 16, 16), (6, 10, 5), (2, 3, 4), (32, 32, 32), (33, 17, 40)])
+# (5, 6, 130), (12, 9, 200), (3, 2, 256): padded z length 512 -> the even/odd-bin z pass (k_z_eo), free space and cathode
+@pytest.mark.parametrize("grid", [(8, 8, 8), (16, 16, 16), (6, 10, 5), (2, 3, 4), (32, 32, 32), (33, 17, 40),
+                                  (5, 6, 130), (12, 9, 200), (3, 2, 256)])
 @pytest.mark.parametrize("at_cathode", [False, True])
 def test_solve_matches_oracle_f64(scb, oracle, record, grid, at_cathode):
     rng = np.random.default_rng(sum(grid))
@@ -135,8 +137,8 @@ def test_solve_matches_oracle_f64(scb, oracle, record, grid, at_cathode):
 
 
 @pytest.mark.parametrize("at_cathode", [False, True])
-def test_solve_matches_oracle_f32(scb, oracle, record, at_cathode):
-    grid = (16, 24, 32)
+@pytest.mark.parametrize("grid", [(16, 24, 32), (7, 5, 140)])
+def test_solve_matches_oracle_f32(scb, oracle, record, at_cathode, grid):
     rng = np.random.default_rng(5)
     rho = rng.standard_normal(grid)
     mesh, ref = _solve_pair(scb, oracle, grid, (-1e-3, -2e-3, 0.5e-3), (1e-3, 1.5e-3, 2.5e-3), 2.0, rho, at_cathode, T=np.float32)
