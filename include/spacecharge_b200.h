@@ -229,9 +229,17 @@ SCB_API int scb_step_strided(scb_handle* h, int64_t np, const void* x, const voi
  *                     runs to the tile with shared-memory atomics and flushes it with coalesced reductions).  Same
  *                     results; measured SLOWER on B200 (shared Float64 atomics are compare-and-swap loops, and an
  *                     ordered bunch makes a CTA's lanes collide on a handful of nodes): kept for comparison only.
+ *   SCB_ORDER_AUTO    the handle decides: every eighth deposit (and whenever the bunch's arrays change) it samples the
+ *                     order (the measurement of scb_particle_order_fraction) and uses the SCB_ORDER_CELL kernels when at
+ *                     least 55 % of the sampled pairs share a cell or are x-neighbours, the SCB_ORDER_RANDOM kernels
+ *                     otherwise; the gather follows the deposit.  For callers that cannot know how ordered their bunch
+ *                     is -- the default kernels are SLOWER on an ordered bunch than on a random one (every lane of a warp
+ *                     reduces into the same node).  The probe synchronises the stream: not usable under stream capture.
  * scb_particle_order_fraction samples neighbouring particle pairs and returns the fraction that share a cell or sit in
  * x-adjacent cells (about 1 for an ordered bunch, about 0 for a random one); synchronous. */
-typedef enum scb_particle_order { SCB_ORDER_RANDOM = 0, SCB_ORDER_CELL = 1, SCB_ORDER_CELL_TILE = 2 } scb_particle_order;
+typedef enum scb_particle_order {
+    SCB_ORDER_RANDOM = 0, SCB_ORDER_CELL = 1, SCB_ORDER_CELL_TILE = 2, SCB_ORDER_AUTO = 3
+} scb_particle_order;
 SCB_API int scb_sort_particles(scb_handle* h, int64_t np, const void* x, const void* y, const void* z, int pdt,
                                int mdt, const int64_t n[3], const double min_bounds[3], const double delta[3],
                                uint32_t* perm_out);

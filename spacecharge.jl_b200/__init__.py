@@ -116,8 +116,10 @@ class Handle:
         self.check(self.lib.scb_drop_green_cache(self.h))
 
     def set_particle_order(self, order):
-        """``"random"`` (default) or ``"cell"``: which kernels the particle passes use (scb_set_particle_order)."""
-        code = {"random": _lib.SCB_ORDER_RANDOM, "cell": _lib.SCB_ORDER_CELL, "cell_tile": _lib.SCB_ORDER_CELL_TILE}.get(order, order)
+        """``"random"`` (default), ``"cell"``, ``"cell_tile"`` or ``"auto"`` (the handle samples the bunch's order every
+        eighth deposit and picks): which kernels the particle passes use (scb_set_particle_order)."""
+        code = {"random": _lib.SCB_ORDER_RANDOM, "cell": _lib.SCB_ORDER_CELL, "cell_tile": _lib.SCB_ORDER_CELL_TILE,
+                "auto": _lib.SCB_ORDER_AUTO}.get(order, order)
         self.check(self.lib.scb_set_particle_order(self.h, int(code)))
 
     def init_comm(self, group):

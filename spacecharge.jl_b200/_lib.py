@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCB_LIB") or os.path.join(HERE, "lib", "libspacecharge_b200.so")
 
 SCB_F32, SCB_F64 = 0, 1
-SCB_ORDER_RANDOM, SCB_ORDER_CELL, SCB_ORDER_CELL_TILE = 0, 1, 2
+SCB_ORDER_RANDOM, SCB_ORDER_CELL, SCB_ORDER_CELL_TILE, SCB_ORDER_AUTO = 0, 1, 2, 3
 SCB_OK = 0
 STATUS_NAMES = {0: "SCB_OK", -1: "SCB_ERR_INVALID_ARG", -2: "SCB_ERR_UNSUPPORTED", -3: "SCB_ERR_CUDA",
                 -4: "SCB_ERR_NO_DEVICE", -5: "SCB_ERR_ALLOC", -6: "SCB_ERR_COMM"}

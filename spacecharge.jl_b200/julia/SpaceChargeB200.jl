@@ -468,6 +468,7 @@ end
 # ---- bunches kept ordered by cell (extension; scb_sort_particles, scb_permute, scb_set_particle_order) -------------
 const SCB_ORDER_RANDOM = Cint(0)
 const SCB_ORDER_CELL = Cint(1)
+const SCB_ORDER_AUTO = Cint(3)
 
 """
     sort_particles(mesh, x, y, z) -> perm::CuVector{UInt32}
@@ -514,12 +515,14 @@ function sort_particles!(mesh::Mesh3D, x::CuVector, y::CuVector, z::CuVector, ot
 end
 
 """
-    set_particle_order!(mesh, order)    order = :random (default kernels) or :cell (run-accumulating kernels)
+    set_particle_order!(mesh, order)    order = :random (default kernels), :cell (run-accumulating kernels) or :auto
+                                        (the handle samples the order every eighth deposit and picks)
 
 Results do not depend on the setting; only the speed of `deposit!`, `interpolate_field` and `step!` does.
 """
 function set_particle_order!(mesh::Mesh3D, order::Symbol)
-    code = order === :cell ? SCB_ORDER_CELL : order === :random ? SCB_ORDER_RANDOM : error("order must be :random or :cell")
+    code = order === :cell ? SCB_ORDER_CELL : order === :random ? SCB_ORDER_RANDOM : order === :auto ? SCB_ORDER_AUTO :
+           error("order must be :random, :cell or :auto")
     h = handle(mesh)
     check(h, ccall((:scb_set_particle_order, LIB), Cint, (Ptr{Cvoid}, Cint), h.ptr, code))
 end

@@ -189,3 +189,42 @@ def test_interpolate_kick_in_cell_order(scb):
         scb.set_particle_order(mesh, "random")
     for got, base, e, c in zip(p, p0, (ex, ey, ez), (0.25e-9, 0.25e-9, 1e-9)):
         assert torch.allclose(got, base + c * e, rtol=1e-14, atol=0)
+
+
+def test_auto_order_picks_the_kernel_family_and_keeps_the_result(scb):
+    """SCB_ORDER_AUTO: same results as the explicit settings on a random and on an ordered bunch, and the ordered bunch
+    must not fall into the default kernels' slow case (every lane of a warp reducing into one node)."""
+    import torch
+    x, y, z, q = gaussian(2_000_000, 12)
+    dev = to_dev(x, y, z, q)
+    mesh = scb.Mesh3D((64, 64, 64), *dev[:3])
+    _, sx, sy, sz, sq = scb.sort_particles_(mesh, *dev)
+    outs = [torch.empty_like(sx) for _ in range(3)]
+    ref = {}
+    for name, bunch in (("random", dev), ("ordered", (sx, sy, sz, sq))):
+        scb.set_particle_order(mesh, "random")
+        scb.step_(mesh, *bunch, *outs)
+        ref[name] = (mesh.rho.clone(), [o.clone() for o in outs])
+    scb.set_particle_order(mesh, "auto")
+    try:
+        for name, bunch in (("random", dev), ("ordered", (sx, sy, sz, sq)), ("random", dev)):
+            for _ in range(3):
+                scb.step_(mesh, *bunch, *outs)
+            assert rel(mesh.rho.cpu().numpy(), ref[name][0].cpu().numpy()) < 1e-13
+            for a, b in zip(outs, ref[name][1]):
+                assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
+        # the choice shows in the deposit time of the ordered bunch: run-accumulating kernels, not 8 colliding reductions
+        hd = mesh.handle
+        hd.enable_timing(True)
+        t = {}
+        for name, order in (("auto", "auto"), ("random", "random"), ("cell", "cell")):
+            scb.set_particle_order(mesh, order)
+            best = 1e9
+            for _ in range(4):
+                scb.step_(mesh, sx, sy, sz, sq, *outs)
+                best = min(best, hd.timing()["deposit_ms"])
+            t[name] = best
+        hd.enable_timing(False)
+        assert t["auto"] < 0.5 * (t["random"] + t["cell"]), t
+    finally:
+        scb.set_particle_order(mesh, "random")
