@@ -769,7 +769,7 @@ bool z_tma_enabled() {
 }
 
 // planes per chunk of the B2 -> B3 hand-over through the L2 (0 = off: one launch each, D through HBM)
-int zchunk_planes(const Plan& pl) {
+int zchunk_planes(const Plan& /*pl*/) {
     static const int env = [] { const char* e = std::getenv("SCB_ZCHUNK"); return e ? std::atoi(e) : -1; }();
     if (env >= 0) return env;
     return 0;

@@ -364,7 +364,7 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
     constexpr int TX = LY::TX;
     constexpr int TPL = N / 8;
     constexpr int SR = LY::SR;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_tma[];
     const int tx = threadIdx.x, j = threadIdx.y;
     const bool leader = (tx == 0 && j == 0);
     const int kx0 = blockIdx.x * TX;
@@ -376,10 +376,10 @@ k_z_tma(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtens
     const int ky = kyl;
     const int Lyh = p.Ly / 2;
     const int kyf = ky <= Lyh ? ky : p.Ly - ky;
-    LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_raw), tx);
-    auto tile = [&](int b) { return reinterpret_cast<C*>(smem_raw + LY::EX + (size_t)b * LY::TILE); };
-    auto sbuf = [&](int b) { return reinterpret_cast<T*>(smem_raw + LY::EX + 2 * LY::TILE + (size_t)b * LY::SB); };
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + LY::BARS);   // [0] input, [1],[2] spectrum
+    LayoutRows<C, TX> lay(reinterpret_cast<C*>(smem_tma), tx);
+    auto tile = [&](int b) { return reinterpret_cast<C*>(smem_tma + LY::EX + (size_t)b * LY::TILE); };
+    auto sbuf = [&](int b) { return reinterpret_cast<T*>(smem_tma + LY::EX + 2 * LY::TILE + (size_t)b * LY::SB); };
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_tma + LY::BARS);   // [0] input, [1],[2] spectrum
     const unsigned tile_bytes = (unsigned)p.nz * TX * sizeof(C);
     const unsigned s_bytes = 2u * SR * TX * sizeof(T);
 
@@ -891,21 +891,21 @@ __global__ void __launch_bounds__((N / 8) * lp_for(N)) k_x_r2c(const XParams<T> 
             if (va) dst[(la + p.line0) * p.split] = cmake<C>(v[4].x, 0);
             if (vb) dst[(lb + p.line0) * p.split] = cmake<C>(v[4].y, 0);
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = j + q * TPL;
-        const C zk = v[q];
-        const C zm = lay.ld((N - k) & (N - 1));
-        const C A = cmake<C>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
-        const C B = cmake<C>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
-        if (va) oa[k] = A;
-        if (vb) ob[k] = B;
-    }
-    if (j == 0) {  // Nyquist bin N/2 lives in v[4] of thread 0
-        if (va) oa[N / 2] = cmake<C>(v[4].x, 0);
-        if (vb) ob[N / 2] = cmake<C>(v[4].y, 0);
+        for (int q = 0; q < 4; ++q) {
+            const int k = j + q * TPL;
+            const C zk = v[q];
+            const C zm = lay.ld((N - k) & (N - 1));
+            const C A = cmake<C>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+            const C B = cmake<C>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
+            if (va) oa[k] = A;
+            if (vb) ob[k] = B;
+        }
+        if (j == 0) {  // Nyquist bin N/2 lives in v[4] of thread 0
+            if (va) oa[N / 2] = cmake<C>(v[4].x, 0);
+            if (vb) ob[N / 2] = cmake<C>(v[4].y, 0);
+        }
     }
 }
 
